@@ -1,0 +1,459 @@
+// conv_gemm.cuh — device kernels for every convolution-shaped op of the U-Net, as tcgen05 implicit GEMMs.
+//
+//   conv_gemm_kernel<BN, BK, B_MN>   forward convs / transposed convs / data gradients
+//       D[pixel, n] = sum over taps t, channels k:  A_t[pixel + off_t, k] * B_t[n, k]
+//       A tiles: NHWC bf16 activations fetched by 4-D tiled TMA boxes (channels, bw, bh, bn) placed at the tap
+//       offset — out-of-bounds rows/columns are zero-filled by the TMA unit, which IS the conv zero padding.
+//       B tiles: bf16 weights [tap][cout][cin]; K-major for forward, MN-major (same storage) for dgrad.
+//       Accumulator: 128 x BN fp32 in TMEM.  Epilogue: bias / ReLU / ReLU-mask / BN-statistics, bf16, TMA store
+//       (or TMA reduce-add for gradient accumulation).
+//
+//   wgrad_kernel<BN>                 weight gradients
+//       dW_t[co, ci] += sum over pixels: dY[pixel + offA_t, co] * X[pixel + offB_t, ci]
+//       both operands MN-major (the pixel axis is GEMM-K), split-K over pixel tiles, fp32 red.add epilogue.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#pragma once
+#include "tc.cuh"
+
+namespace mcb {
+
+constexpr int kMaxTaps = 24;
+constexpr int kGemmThreads = 192;
+
+struct TapDesc {
+  int16_t src;      // index into tmA
+  int16_t dx, dy;   // offset in the source view (W, H coordinates)
+  int16_t nchunks;  // number of BK-channel chunks of this source
+  int32_t wk0;      // first K coordinate in the weight tensor for this source (concat offset)
+  int32_t wtap;     // tap coordinate in the weight tensor
+};
+
+struct ConvGemmParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  CUtensorMap tmD[4];  // one per phase (blockIdx.z)
+  TapDesc taps[kMaxTaps];
+  int tap_start[4];
+  int tap_count[4];
+  int Wv, Hv, Nimg;  // extents of the output view
+  int bw, bh, bn, rows;
+  int tiles_x, tiles_y;
+  int stages;
+  int n_off;  // first N (weight row / column) coordinate of this launch (concat source slice for dgrad)
+  // epilogue
+  const float* bias;
+  float* stats;
+  int stats_c;  // number of channels in stats (cout)
+  const __nv_bfloat16* mask;  // ReLU mask tensor (NHWC, full-resolution output tensor), or null
+  int mask_H, mask_W, mask_C, mask_s;  // full dims; mask_s = 1 (plain) or 2 (output is a parity view)
+  int relu;
+  int accumulate;
+};
+
+struct WgradTap {
+  int16_t srcA, ax, ay;
+  int16_t srcB, bx, by;
+  int32_t wtap;
+};
+
+struct WgradParams {
+  CUtensorMap tmA[4];  // dY views, box (64 | 32 channels, bw, bh, bn)
+  CUtensorMap tmB[4];  // X views
+  WgradTap taps[16];
+  int ntaps;
+  int Wv, Hv, Nimg;
+  int bw, bh, bn, rows;  // rows % 16 == 0, rows <= 64
+  int tiles_x, tiles_y, tiles_total;
+  int splits;
+  int stages;
+  float* dw;  // [tap][cout][cin_total]
+  int cout, cin_total, ci_off;
+  int a_cw;  // channel width of one A chunk: 64 (SW128) or 32 (SW64)
+  int a_chunks;  // chunks actually loaded (1 or 2); missing ones alias chunk 0 (LBO = 0)
+};
+
+__device__ __forceinline__ uint8_t* align_up_1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// -------------------------------------------------------------------------------------------------
+template <int BN, int BK, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  static_assert(BK == 64 || BK == 32, "BK");
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+  constexpr int A_ROW_BYTES = BK * 2;              // 128 (SW128) or 64 (SW64)
+  constexpr int A_BYTES = 128 * A_ROW_BYTES;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t A_LAYOUT = (BK == 64) ? tc::LAYOUT_SW128 : tc::LAYOUT_SW64;
+  // MN-major B: rows are K (BK of them), each row holds min(BN,64) n-values
+  constexpr int BMN_CW = (BN >= 64) ? 64 : 32;          // n-values per sub-tile row
+  constexpr int BMN_ROW_BYTES = BMN_CW * 2;             // 128 or 64
+  constexpr int BMN_SUB_BYTES = BK * BMN_ROW_BYTES;     // one sub-tile
+  constexpr int BMN_SUBS = BN / BMN_CW;
+  constexpr uint32_t BMN_LAYOUT = (BMN_CW == 64) ? tc::LAYOUT_SW128 : tc::LAYOUT_SW64;
+  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, BN, 0, B_MN ? 1 : 0);
+  // output staging: chunks of OUT_CW channels
+  constexpr int OUT_CW = (BN >= 64) ? 64 : 32;
+  constexpr int OUT_ROW_BYTES = OUT_CW * 2;
+  constexpr int OUT_CHUNK_BYTES = 128 * OUT_ROW_BYTES;
+  constexpr int OUT_CHUNKS = BN / OUT_CW;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_up_1024(smem_raw);
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* row_valid = reinterpret_cast<uint8_t*>(tmem_slot + 2);  // 128 bytes
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int phase_id = blockIdx.z;
+  const int mt = blockIdx.x;
+  const int tx = mt % p.tiles_x;
+  const int ty = (mt / p.tiles_x) % p.tiles_y;
+  const int tn = mt / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+  const int ncol0 = blockIdx.y * BN;
+
+  const int tap_begin = p.tap_start[phase_id];
+  const int tap_end = tap_begin + p.tap_count[phase_id];
+  int num_kb = 0;
+  for (int t = tap_begin; t < tap_end; ++t) num_kb += p.taps[t].nchunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    tc::mbar_init(tmem_full_bar, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&p.tmB);
+    tc::prefetch_tmap(&p.tmD[phase_id]);
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, BN);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)p.rows * A_ROW_BYTES;
+      int kb = 0;
+      for (int t = tap_begin; t < tap_end; ++t) {
+        const TapDesc tap = p.taps[t];
+        const CUtensorMap* mA = &p.tmA[tap.src];
+        for (int ch = 0; ch < tap.nchunks; ++ch, ++kb) {
+          const int s = kb % stages;
+          const uint32_t ph = (kb / stages) & 1;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          tc::mbar_expect_tx(&full_bar[s], a_bytes + B_BYTES);
+          tc::tma_load_4d(sa, mA, &full_bar[s], ch * BK, x0 + tap.dx, y0 + tap.dy, n0);
+          if (!B_MN) {
+            // box (BK k, BN rows, 1 tap)
+            tc::tma_load_3d(sb, &p.tmB, &full_bar[s], tap.wk0 + ch * BK, p.n_off + ncol0, tap.wtap);
+          } else {
+            // weight viewed as (cin inner = N, cout = K rows, tap): BMN_SUBS boxes of (BMN_CW, BK, 1)
+#pragma unroll
+            for (int j = 0; j < BMN_SUBS; ++j)
+              tc::tma_load_3d(sb + j * BMN_SUB_BYTES, &p.tmB, &full_bar[s], p.n_off + ncol0 + j * BMN_CW,
+                              tap.wk0 + ch * BK, tap.wtap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % stages;
+      const uint32_t ph = (kb / stages) & 1;
+      tc::mbar_wait(&full_bar[s], ph);
+      tc::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        const uint64_t da0 = tc::make_smem_desc(sa, 16, 8 * A_ROW_BYTES, A_LAYOUT);
+        uint64_t db0;
+        if (!B_MN) db0 = tc::make_smem_desc(sb, 16, 8 * A_ROW_BYTES, A_LAYOUT);
+        else db0 = tc::make_smem_desc(sb, BMN_SUB_BYTES, 8 * BMN_ROW_BYTES, BMN_LAYOUT);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = da0 + (uint64_t)((k * 32) >> 4);
+          const uint64_t db = B_MN ? db0 + (uint64_t)((k * 16 * BMN_ROW_BYTES) >> 4) : db0 + (uint64_t)((k * 32) >> 4);
+          tc::umma_bf16(tmem_base, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::umma_commit(&empty_bar[s]);
+        if (kb == num_kb - 1) tc::umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int wi = row % p.bw;
+    const int hi = (row / p.bw) % p.bh;
+    const int ni = row / (p.bw * p.bh);
+    const int ox = x0 + wi, oy = y0 + hi, on = n0 + ni;
+    const bool valid = row < p.rows && ox < p.Wv && oy < p.Hv && on < p.Nimg;
+    row_valid[row] = valid ? 1 : 0;
+
+    const __nv_bfloat16* mrow = nullptr;
+    if (p.mask != nullptr && valid) {
+      const int fy = oy * p.mask_s + (p.mask_s == 2 ? (phase_id >> 1) : 0);
+      const int fx = ox * p.mask_s + (p.mask_s == 2 ? (phase_id & 1) : 0);
+      mrow = p.mask + (((size_t)on * p.mask_H + fy) * p.mask_W + fx) * p.mask_C + p.n_off + ncol0;
+    }
+
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::tc_fence_after();
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + p.n_off + ncol0 + c0 + i);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      if (mrow != nullptr) {
+        const uint4* mp = reinterpret_cast<const uint4*>(mrow + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 m = __ldg(mp + j);
+          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            // bf16 > 0  <=>  sign bit clear and magnitude nonzero
+            const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
+            if (!(lo != 0 && lo < 0x8000u)) f[j * 8 + e * 2] = 0.f;
+            if (!(hi2 != 0 && hi2 < 0x8000u)) f[j * 8 + e * 2 + 1] = 0.f;
+          }
+        }
+      }
+      // stage as bf16 into the swizzled output tile: chunk (c0 / OUT_CW), 16-byte units within the row
+      const int chunk = c0 / OUT_CW;
+      const int unit0 = (c0 % OUT_CW) / 8;  // first 16B unit of these 32 channels inside the row
+      uint8_t* rowp = smem + (size_t)chunk * OUT_CHUNK_BYTES + (size_t)row * OUT_ROW_BYTES;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = tc::pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+        o.y = tc::pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+        o.z = tc::pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+        o.w = tc::pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+        int unit = unit0 + j;
+        if (OUT_CW == 64) unit ^= (row & 7);          // SWIZZLE_128B
+        else unit ^= ((row >> 1) & 3);                // SWIZZLE_64B
+        *reinterpret_cast<uint4*>(rowp + unit * 16) = o;
+      }
+    }
+    tc::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    if (p.stats != nullptr) {
+      // per-channel sum / sum of squares of the bf16-rounded outputs over the valid rows of this tile
+      const int et = threadIdx.x - 64;  // 0..127
+      constexpr int GROUPS = 128 / OUT_CW;
+      constexpr int ROWS_PER_GROUP = 128 / GROUPS;
+      const int c = et % OUT_CW;
+      const int g = et / OUT_CW;
+      for (int chunk = 0; chunk < OUT_CHUNKS; ++chunk) {
+        float s1 = 0.f, s2 = 0.f;
+        const uint8_t* cb = smem + (size_t)chunk * OUT_CHUNK_BYTES;
+        for (int r = g * ROWS_PER_GROUP; r < (g + 1) * ROWS_PER_GROUP; ++r) {
+          if (row_valid[r]) {
+            int unit = c >> 3;
+            if (OUT_CW == 64) unit ^= (r & 7);
+            else unit ^= ((r >> 1) & 3);
+            const __nv_bfloat16 hv =
+                *reinterpret_cast<const __nv_bfloat16*>(cb + (size_t)r * OUT_ROW_BYTES + unit * 16 + (c & 7) * 2);
+            const float x = __bfloat162float(hv);
+            s1 += x;
+            s2 += x * x;
+          }
+        }
+        const int ch = p.n_off + ncol0 + chunk * OUT_CW + c;
+        atomicAdd(p.stats + ch, s1);
+        atomicAdd(p.stats + p.stats_c + ch, s2);
+      }
+    }
+
+    if (warp == 2 && lane == 0) {
+      const CUtensorMap* mD = &p.tmD[phase_id];
+#pragma unroll
+      for (int chunk = 0; chunk < OUT_CHUNKS; ++chunk) {
+        const void* src = smem + (size_t)chunk * OUT_CHUNK_BYTES;
+        if (p.accumulate) tc::tma_reduce_add_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+        else tc::tma_store_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+      }
+      tc::tma_store_commit();
+      tc::tma_store_wait_read0();
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+  constexpr int KROWS = 64;                       // max pixel rows per K block
+  constexpr int B_CW = (BN >= 64) ? 64 : 32;      // channels per B sub-tile row
+  constexpr int B_ROW_BYTES = B_CW * 2;
+  constexpr int B_SUB_BYTES = KROWS * B_ROW_BYTES;
+  constexpr int B_SUBS = BN / B_CW;
+  constexpr int B_BYTES = B_SUBS * B_SUB_BYTES;
+  constexpr uint32_t B_LAYOUT = (B_CW == 64) ? tc::LAYOUT_SW128 : tc::LAYOUT_SW64;
+  constexpr int A_SUB_BYTES = KROWS * 128;        // sized for the 64-channel case
+  constexpr int A_BYTES = 2 * A_SUB_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, BN, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_up_1024(smem_raw);
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ncol0 = blockIdx.x * BN;       // cin tile
+  const int m0 = blockIdx.y * 128;         // cout tile
+  const int tap_id = blockIdx.z / p.splits;
+  const int split = blockIdx.z % p.splits;
+  const WgradTap tap = p.taps[tap_id];
+  // K blocks (pixel tiles) of this split
+  const int per = (p.tiles_total + p.splits - 1) / p.splits;
+  const int kb_begin = split * per;
+  const int kb_end = min(p.tiles_total, kb_begin + per);
+  const int num_kb = max(0, kb_end - kb_begin);
+  const int a_row_bytes = p.a_cw * 2;
+  const uint32_t a_layout = (p.a_cw == 64) ? tc::LAYOUT_SW128 : tc::LAYOUT_SW64;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    tc::mbar_init(tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, BN);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* mA = &p.tmA[tap.srcA];
+        const CUtensorMap* mB = &p.tmB[tap.srcB];
+        const uint32_t tx_bytes = (uint32_t)p.rows * (uint32_t)(a_row_bytes * p.a_chunks + B_ROW_BYTES * B_SUBS);
+        for (int i = 0; i < num_kb; ++i) {
+          const int kb = kb_begin + i;
+          const int s = i % stages;
+          const uint32_t ph = (i / stages) & 1;
+          const int tx = kb % p.tiles_x;
+          const int ty = (kb / p.tiles_x) % p.tiles_y;
+          const int tn = kb / (p.tiles_x * p.tiles_y);
+          const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          tc::mbar_expect_tx(&full_bar[s], tx_bytes);
+          for (int j = 0; j < p.a_chunks; ++j)
+            tc::tma_load_4d(sa + j * A_SUB_BYTES, mA, &full_bar[s], m0 + j * p.a_cw, x0 + tap.ax, y0 + tap.ay, n0);
+#pragma unroll
+          for (int j = 0; j < B_SUBS; ++j)
+            tc::tma_load_4d(sb + j * B_SUB_BYTES, mB, &full_bar[s], ncol0 + j * B_CW, x0 + tap.bx, y0 + tap.by, n0);
+        }
+      }
+    } else if (warp == 1) {
+      const int ksteps = p.rows / 16;
+      // A: M = 128 = (128 / a_cw) chunks of a_cw channels; chunks beyond a_chunks alias chunk 0 via LBO = 0
+      const uint32_t a_lbo = (p.a_chunks * p.a_cw >= 128) ? (uint32_t)A_SUB_BYTES : 0u;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da0 = tc::make_smem_desc(sa, a_lbo, 8 * a_row_bytes, a_layout);
+          const uint64_t db0 = tc::make_smem_desc(sb, B_SUB_BYTES, 8 * B_ROW_BYTES, B_LAYOUT);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = da0 + (uint64_t)((k * 16 * a_row_bytes) >> 4);
+            const uint64_t db = db0 + (uint64_t)((k * 16 * B_ROW_BYTES) >> 4);
+            tc::umma_bf16(tmem_base, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[s]);
+          if (i == num_kb - 1) tc::umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = m0 + q * 32 + lane;
+      const bool valid = (q * 32 + lane) < p.a_chunks * p.a_cw && co < p.cout;
+      tc::mbar_wait(tmem_full_bar, 0);
+      tc::tc_fence_after();
+      float* drow = p.dw + ((size_t)tap.wtap * p.cout + (valid ? co : 0)) * p.cin_total + p.ci_off + ncol0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + i),
+                         "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])),
+                         "f"(__uint_as_float(v[i + 3]))
+                         : "memory");
+          }
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace mcb
