@@ -111,6 +111,77 @@ typedef struct {
 } mcb_convt_wgrad_args;
 int mcb_convt_wgrad(const mcb_convt_wgrad_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * HBM-bound glue kernels of the train / inference step (16-byte vectorised NHWC bf16 passes).
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* API-edge layout conversion: the reference hands the net NCHW fp32 (src/steps/pytorch/models.py:76-92) */
+int mcb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, void* stream);
+int mcb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, int c, int h, int w, void* stream);
+
+/* ResNet stem, encoder.conv1 = Conv2d(3, 64, 7, stride 2, pad 3) (src/unet_models.py:360): im2col into a
+ * [n*h/2*w/2][192] bf16 matrix (k = (ky*7+kx)*3 + c, zero-padded 147 -> 192) fed to mcb_conv_fwd as a 1x1 conv.
+ * The master weight is fp32 [49][64][3]; pack/unpack convert to/from the GEMM operand [64][192]. */
+int mcb_stem_im2col(const float* x_nchw, void* col, int n, int h, int w, void* stream);
+int mcb_stem_pack_weight(const float* w, void* w_packed, void* stream);
+int mcb_stem_unpack_wgrad(const float* dw_packed, float* dw, void* stream); /* dw += */
+
+/* nn.BatchNorm2d (eps 1e-5, momentum 0.1; torchvision resnet blocks).  Training: `stats` is what mcb_conv_fwd
+ * accumulated; finalize turns it into the per-channel affine + saved mean / invstd and updates the running stats. */
+int mcb_bn_finalize(const float* stats, long count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, float* scale, float* shift, float* mean,
+                    float* invstd, int c, void* stream);
+int mcb_bn_eval_params(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift, int c, void* stream);
+/* y = [relu](z*scale + shift [+ residual*res_scale + res_shift | + residual]) — BN + residual add + ReLU in one pass */
+int mcb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, const float* res_scale,
+                 const float* res_shift, int relu, void* y, long pixels, int c, void* stream);
+/* backward: g = dy * (y_mask > 0);  dbeta += sum g;  dgamma += sum g * xhat */
+int mcb_bn_bwd_reduce(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
+                      float* dbeta, float* dgamma, long pixels, int c, void* stream);
+/* dz = gamma*invstd*(g - dbeta/M - xhat*dgamma/M); g_out (optional) receives g (= or +=) for the residual branch */
+int mcb_bn_bwd_apply(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
+                     const float* gamma, const float* dbeta, const float* dgamma, void* dz, void* g_out,
+                     int g_accumulate, long pixels, int c, void* stream);
+/* out[c] += sum over pixels of x[.., c]  (conv bias gradients) */
+int mcb_channel_sum(const void* x, float* out, long pixels, int c, void* stream);
+
+/* nn.MaxPool2d(2, 2) (src/unet_models.py:356,363,392); backward routes to the first maximum like torch */
+int mcb_maxpool2_fwd(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int mcb_maxpool2_bwd(const void* x, const void* dy, void* dx, int accumulate, int n, int h, int w, int c,
+                     void* stream);
+
+/* final = Conv2d(32, 2, 1) (src/unet_models.py:383,403): NHWC bf16 -> NCHW fp32 logits; backward also applies
+ * dec0's ReLU mask (x is dec0's output) */
+int mcb_final_conv_fwd(const void* x, const float* w, const float* b, float* logits, int n, int h, int wd, int c, int k,
+                       void* stream);
+int mcb_final_conv_bwd(const void* x, const float* w, const float* dlogits, void* dx, float* dw, float* db, int n,
+                       int h, int wd, int c, int k, void* stream);
+
+/* torch.optim.Adam with L2 (src/models.py:57,287-292) over one flat fp32 arena; refreshes the bf16 operand copy */
+int mcb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+int mcb_cast_f32_bf16(const float* x, void* y, long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Losses (src/models.py:310-454, src/steps/pytorch/validation.py:8-28), two phases around the global sums
+ * sums[4] = { sum p1*t, sum p1, sum t, sum w*ce } (fp64, zero before phase 1, all-reduce between phases under DDP).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* logits; /* fp32 NCHW [n][2][h][w] */
+  const float* target; /* fp32 NCHW [n][3][h][w] (mask, distance, size) for mode 0; [n][1][h][w] for mode 1 */
+  int n, h, w;
+  int mode;            /* 0: PyTorchUNetWeighted (weighted CE + Dice); 1: PyTorchUNet (plain CE) */
+  float w0, sigma;     /* neptune.yaml:55-56 */
+  float size_c;        /* C = sqrt(image_h*image_w)/2 from the CONFIGURED size (src/models.py:373-381) */
+  float dice_weight, ce_weight, dice_smooth;
+} mcb_loss_args;
+int mcb_loss_partials(const mcb_loss_args* a, double* sums, void* stream);
+int mcb_loss_grad(const mcb_loss_args* a, const double* sums, long global_pixels, float grad_scale, float* dlogits,
+                  float* loss_out, void* stream);
+/* numpy softmax over the class axis (src/utils.py:231-273 at src/models.py:88-92) */
+int mcb_softmax2(const float* logits, float* probs, int n, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

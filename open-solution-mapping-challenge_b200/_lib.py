@@ -68,3 +68,51 @@ def call(name, args=None, *extra):
     else:
         rc = fn(C.byref(args), *extra, stream_ptr())
     check(rc, name)
+
+
+class LossArgs(C.Structure):
+    _fields_ = [("logits", vp), ("target", vp), ("n", ci), ("h", ci), ("w", ci), ("mode", ci), ("w0", C.c_float),
+                ("sigma", C.c_float), ("size_c", C.c_float), ("dice_weight", C.c_float), ("ce_weight", C.c_float),
+                ("dice_smooth", C.c_float)]
+
+
+cl, cf = C.c_long, C.c_float
+_SIGS = {
+    "mcb_nchw_f32_to_nhwc_bf16": [vp, vp, ci, ci, ci, ci, vp],
+    "mcb_nhwc_bf16_to_nchw_f32": [vp, vp, ci, ci, ci, ci, vp],
+    "mcb_stem_im2col": [vp, vp, ci, ci, ci, vp],
+    "mcb_stem_pack_weight": [vp, vp, vp],
+    "mcb_stem_unpack_wgrad": [vp, vp, vp],
+    "mcb_bn_finalize": [vp, cl, vp, vp, vp, vp, cf, cf, vp, vp, vp, vp, ci, vp],
+    "mcb_bn_eval_params": [vp, vp, vp, vp, cf, vp, vp, ci, vp],
+    "mcb_bn_apply": [vp, vp, vp, vp, vp, vp, ci, vp, cl, ci, vp],
+    "mcb_bn_bwd_reduce": [vp, vp, vp, vp, vp, vp, vp, cl, ci, vp],
+    "mcb_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, cl, ci, vp],
+    "mcb_channel_sum": [vp, vp, cl, ci, vp],
+    "mcb_maxpool2_fwd": [vp, vp, ci, ci, ci, ci, vp],
+    "mcb_maxpool2_bwd": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "mcb_final_conv_fwd": [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "mcb_final_conv_bwd": [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "mcb_adam_step": [vp, vp, vp, vp, vp, cl, cf, cf, cf, cf, cf, ci, cf, vp],
+    "mcb_cast_f32_bf16": [vp, vp, cl, vp],
+    "mcb_loss_partials": [C.POINTER(LossArgs), vp, vp],
+    "mcb_loss_grad": [C.POINTER(LossArgs), vp, cl, cf, vp, vp, vp],
+    "mcb_softmax2": [vp, vp, ci, ci, ci, vp],
+}
+for _n, _a in _SIGS.items():
+    getattr(lib, _n).argtypes = _a
+    getattr(lib, _n).restype = ci
+for _n in ("mcb_conv_fwd", "mcb_conv_dgrad", "mcb_conv_wgrad", "mcb_convt_fwd", "mcb_convt_dgrad", "mcb_convt_wgrad"):
+    getattr(lib, _n).restype = ci
+
+
+def dp(t):
+    """raw device pointer (int) of a tensor, or None"""
+    return None if t is None else t.data_ptr()
+
+
+def fcall(name, *args):
+    """call a flat-signature entry point, appending the current stream"""
+    import torch
+    rc = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+    check(rc, name)

@@ -1,0 +1,391 @@
+"""Static launch plans for UNetResNet: every kernel launch of one forward (and its backward) over preallocated
+NHWC bf16 buffers, replayable as CUDA graphs.
+
+Data flow per conv+BN unit in training:  z = conv(a_prev) [+ per-channel sum / sumsq in the GEMM epilogue]
+-> bn_finalize (batch statistics, running-stat update) -> a = relu(z*scale + shift [+ residual]) in one pass.
+Backward mirrors torch autograd of /root/reference/src/unet_models.py:385-403: per unit a reduction
+(dbeta, dgamma with the ReLU mask folded in), one elementwise pass producing dz, then the tcgen05 dgrad and
+split-K wgrad GEMMs; decoder ReLU masks are applied in the dgrad epilogues; skip-connection gradients are
+accumulated with TMA reduce-add."""
+import torch
+from torch import nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+class _BN:
+    """per-BatchNorm device state"""
+    __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta")
+
+
+class Plan:
+    def __init__(self, net, n, h, w, training):
+        self.net, self.n, self.h, self.w, self.training = net, n, h, w, training
+        self.dev = net._p32.device
+        self.fwd_ops = []          # closures, in order
+        self.bwd_layers = []       # list of lists of closures (one list per forward unit), executed in reverse
+        self.grad = {}             # id(activation) -> gradient buffer
+        self.written = set()       # gradient buffers that already hold a contribution
+        self._keep = []            # keeps tensors referenced by closures alive
+        self._bns = []
+        self._bwd_builders = []    # one per forward unit; run in REVERSE so store/accumulate modes follow run order
+        total_c = sum(m.num_features for m in net.modules() if isinstance(m, nn.BatchNorm2d))
+        self._stats_arena = torch.zeros(2 * total_c, dtype=F32, device=self.dev)
+        self._stats_used = 0
+        self.graph_fwd = self.graph_bwd = None
+        self.x_in = torch.zeros((n, 3, h, w), dtype=F32, device=self.dev)
+        self.dlogits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
+        self.logits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
+        self._build()
+        for builder in reversed(self._bwd_builders):
+            B = []
+            builder(B)
+            self.bwd_layers.append(B)
+        self.launches_fwd = len(self.fwd_ops)
+        self.launches_bwd = sum(len(l) for l in self.bwd_layers)
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def act(self, n, h, w, c):
+        t = torch.zeros((n, h, w, c), dtype=BF16, device=self.dev)
+        self._keep.append(t)
+        return t
+
+    def gbuf(self, a):
+        g = self.grad.get(id(a))
+        if g is None:
+            g = torch.zeros_like(a)
+            self.grad[id(a)] = g
+            self._keep.append(g)
+        return g
+
+    def gmode(self, a):
+        """-> accumulate flag for the next writer of grad(a); marks it written"""
+        acc = id(a) in self.written
+        self.written.add(id(a))
+        return acc
+
+    def bn_state(self, mod):
+        net = self.net
+        b = _BN()
+        b.mod, b.c = mod, mod.num_features
+        c = b.c
+        buf = torch.zeros(4 * c, dtype=F32, device=self.dev)
+        self._keep.append(buf)
+        b.stats = self._stats_arena[self._stats_used:self._stats_used + 2 * c]
+        self._stats_used += 2 * c
+        b.scale, b.shift, b.mean, b.invstd = buf[:c], buf[c:2 * c], buf[2 * c:3 * c], buf[3 * c:4 * c]
+        b.gamma, b.beta = net._vec(mod.weight, net._p32), net._vec(mod.bias, net._p32)
+        b.dgamma, b.dbeta = net._vec(mod.weight, net._g32), net._vec(mod.bias, net._g32)
+        self._bns.append(b)
+        return b
+
+    # one conv (+BN) unit ------------------------------------------------------------------------------
+    def conv_bn(self, x, conv, bnmod, relu, residual=None, res_bn=None, out=None):
+        """z = conv(x); y = [relu](bn(z) [+ residual | + res_bn(residual_raw)]).  Returns (y, z, bn).  When `relu` is
+        None the BN apply is deferred (the caller fuses it into a later residual pass) and y is None."""
+        net = self.net
+        k, s = conv.kernel_size[0], conv.stride[0]
+        n, h, w, cin = x.shape
+        cout = conv.out_channels
+        z = self.act(n, h // s, w // s, cout)
+        bn = self.bn_state(bnmod)
+        w16 = net._packed(conv.weight, net._w16)
+        F = self.fwd_ops
+        if self.training:
+            F.append(lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z))
+            cnt = z.numel() // cout
+            F.append(lambda: ops.bn_finalize(bn.stats, cnt, bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var,
+                                             bn.scale, bn.shift, bn.mean, bn.invstd, BN_MOMENTUM, BN_EPS))
+        else:
+            F.append(lambda: ops.conv_fwd(x, w16, k, s, out=z))
+            F.append(lambda: ops.bn_eval_params(bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var, bn.scale,
+                                                bn.shift, BN_EPS))
+        if relu is None:
+            return None, z, bn
+        y = out if out is not None else self.act(*z.shape)
+        if res_bn is not None:
+            rb = res_bn
+            F.append(lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, rb.scale, rb.shift))
+        else:
+            F.append(lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual))
+        return y, z, bn
+
+    def conv_unit_backward(self, B, dy, ymask, z, bn, conv, x, g_out=None, g_out_acc=False):
+        """backward of y = relu(bn(conv(x)) [+ r]) given dy = dL/dy: BN reductions + dz, wgrad, dgrad into grad(x).
+        g_out receives g = dy*(y>0) for a residual branch."""
+        net = self.net
+        k, s = conv.kernel_size[0], conv.stride[0]
+        dz = self.act(*z.shape)
+        w16 = net._packed(conv.weight, net._w16)
+        gw = net._packed(conv.weight, net._g32)
+        B.append(lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma))
+        B.append(lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma, dz, g_out,
+                                          g_out_acc))
+        B.append(lambda: ops.conv_wgrad(dz, x, gw, k, s))
+        return dz
+
+    def dgrad_into(self, B, dz, conv, x, relu_mask=None, ci_off=0):
+        """grad(x) (+)= dgrad(dz)"""
+        net = self.net
+        k, s = conv.kernel_size[0], conv.stride[0]
+        w16 = net._packed(conv.weight, net._w16)
+        gx = self.gbuf(x)
+        acc = self.gmode(x)
+        hw = (x.shape[1], x.shape[2])
+        cin = x.shape[3]
+        if acc and relu_mask is not None:
+            raise RuntimeError("plan error: masked dgrad cannot accumulate")
+        B.append(lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
+                                        accumulate=acc, out=gx))
+
+    # ------------------------------------------------------------------------------------------ network
+    def _build(self):
+        net, n, h, w = self.net, self.n, self.h, self.w
+        F = self.fwd_ops
+        enc = net.encoder
+        train = self.training
+
+        # ---- stem: 7x7/s2 conv as im2col + GEMM, BN, ReLU, 2x2 max-pool (src/unet_models.py:360-363)
+        col = self.act(n, h // 2, w // 2, 192)
+        stem_w16 = torch.zeros((1, 64, 192), dtype=BF16, device=self.dev)
+        self._keep.append(stem_w16)
+        stem_master = net._vec(enc.conv1.weight, net._p32)
+        F.append(lambda: ops.stem_im2col(self.x_in, col))
+        F.append(lambda: ops.stem_pack_weight(stem_master, stem_w16))
+        z0 = self.act(n, h // 2, w // 2, 64)
+        bn0 = self.bn_state(enc.bn1)
+        if train:
+            F.append(lambda: ops.conv_fwd(col, stem_w16, 1, 1, stats=bn0.stats, out=z0))
+            cnt0 = z0.numel() // 64
+            F.append(lambda: ops.bn_finalize(bn0.stats, cnt0, bn0.gamma, bn0.beta, enc.bn1.running_mean,
+                                             enc.bn1.running_var, bn0.scale, bn0.shift, bn0.mean, bn0.invstd,
+                                             BN_MOMENTUM, BN_EPS))
+        else:
+            F.append(lambda: ops.conv_fwd(col, stem_w16, 1, 1, out=z0))
+            F.append(lambda: ops.bn_eval_params(bn0.gamma, bn0.beta, enc.bn1.running_mean, enc.bn1.running_var,
+                                                bn0.scale, bn0.shift, BN_EPS))
+        a0 = self.act(*z0.shape)
+        F.append(lambda: ops.bn_apply(z0, bn0.scale, bn0.shift, a0, True))
+        c1 = self.act(n, h // 4, w // 4, 64)
+        F.append(lambda: ops.maxpool2_fwd(a0, c1))
+        if train:
+            def build_stem(B):
+                d_a0 = self.gbuf(a0)
+                d_c1 = self.gbuf(c1)
+                dz0 = self.act(*z0.shape)
+                stem_gw = torch.zeros((1, 64, 192), dtype=F32, device=self.dev)
+                self._keep.append(stem_gw)
+                stem_g = net._vec(enc.conv1.weight, net._g32)
+                B.append(lambda: ops.maxpool2_bwd(a0, d_c1, d_a0, False))
+                B.append(lambda: ops.bn_bwd_reduce(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.dbeta, bn0.dgamma))
+                B.append(lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma, bn0.dbeta,
+                                                  bn0.dgamma, dz0))
+                B.append(lambda: stem_gw.zero_())
+                B.append(lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1))
+                B.append(lambda: ops.stem_unpack_wgrad(stem_gw, stem_g))
+            self._bwd_builders.append(build_stem)
+
+        # ---- encoder stages (torchvision BasicBlock / Bottleneck)
+        x = c1
+        skips = []
+        for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
+            for blk in layer:
+                x = self._res_block(x, blk)
+            skips.append(x)
+        c2, c3, c4, c5 = skips
+
+        # ---- centre + decoder (src/unet_models.py:373-403)
+        pool = self.act(n, c5.shape[1] // 2, c5.shape[2] // 2, c5.shape[3])
+        F.append(lambda: ops.maxpool2_fwd(c5, pool))
+        if train:
+            def build_pool(B):
+                d_pool, d_c5 = self.gbuf(pool), self.gbuf(c5)
+                acc = self.gmode(c5)  # dec5's skip dgrad ran first -> accumulate
+                B.append(lambda: ops.maxpool2_bwd(c5, d_pool, d_c5, acc))
+            self._bwd_builders.append(build_pool)
+        center = self._decoder(pool, None, net.center, pool_input=True)
+        d5 = self._decoder(center, c5, net.dec5)
+        d4 = self._decoder(d5, c4, net.dec4)
+        d3 = self._decoder(d4, c3, net.dec3)
+        d2 = self._decoder(d3, c2, net.dec2)
+        d1 = self._decoder(d2, None, net.dec1)
+        # dec0 = ConvRelu(32, 32)
+        conv0 = net.dec0.conv
+        w0_16 = net._packed(conv0.weight, net._w16)
+        b0 = net._vec(conv0.bias, net._p32)
+        d0 = self.act(n, h, w, conv0.out_channels)
+        F.append(lambda: ops.conv_fwd(d1, w0_16, 3, 1, bias=b0, relu=True, out=d0))
+        fw, fb = net._vec(net.final.weight, net._p32), net._vec(net.final.bias, net._p32)
+        F.append(lambda: ops.final_conv_fwd(d0, fw, fb, self.logits))
+        self.named = dict(conv1=c1, conv2=c2, conv3=c3, conv4=c4, conv5=c5, center=center, dec5=d5, dec4=d4, dec3=d3,
+                          dec2=d2, dec1=d1, dec0=d0)
+        if train:
+            def build_head(B):
+                g_d0 = self.gbuf(d0)
+                gfw, gfb = net._vec(net.final.weight, net._g32), net._vec(net.final.bias, net._g32)
+                # final 1x1 backward also applies dec0's ReLU mask
+                B.append(lambda: ops.final_conv_bwd(d0, fw, self.dlogits, g_d0, gfw, gfb))
+                gb0 = net._vec(conv0.bias, net._g32)
+                gw0 = net._packed(conv0.weight, net._g32)
+                B.append(lambda: ops.channel_sum(g_d0, gb0))
+                B.append(lambda: ops.conv_wgrad(g_d0, d1, gw0, 3, 1))
+                self.dgrad_into(B, g_d0, conv0, d1, relu_mask=d1)
+            self._bwd_builders.append(build_head)
+
+    def _res_block(self, x, blk):
+        """torchvision BasicBlock / Bottleneck forward + backward plan"""
+        train = self.training
+        F = self.fwd_ops
+        is_bottleneck = hasattr(blk, "conv3")
+        convs = [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)] + ([(blk.conv3, blk.bn3)] if is_bottleneck else [])
+        acts = [x]
+        units = []
+        cur = x
+        for conv, bnm in convs[:-1]:
+            y, z, bn = self.conv_bn(cur, conv, bnm, True)
+            units.append((conv, cur, y, z, bn))
+            cur = y
+        conv_l, bn_l = convs[-1]
+        _, z_l, bnl = self.conv_bn(cur, conv_l, bn_l, None)
+        out = self.act(*z_l.shape)
+        if blk.downsample is not None:
+            dconv, dbnm = blk.downsample[0], blk.downsample[1]
+            _, zd, bnd = self.conv_bn(x, dconv, dbnm, None)
+            F.append(lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, zd, bnd.scale, bnd.shift))
+        else:
+            F.append(lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, x))
+        if train:
+            last_in = cur
+
+            def build_block(B):
+                d_out = self.gbuf(out)
+                if blk.downsample is None:
+                    # identity branch: grad(x) (+)= g = d_out * (out > 0), emitted by the last BN's backward pass
+                    gx = self.gbuf(x)
+                    acc = self.gmode(x)
+                    dz_l = self.conv_unit_backward(B, d_out, out, z_l, bnl, conv_l, last_in, g_out=gx, g_out_acc=acc)
+                else:
+                    dz_l = self.conv_unit_backward(B, d_out, out, z_l, bnl, conv_l, last_in)
+                # walk back through the inner units
+                dz = dz_l
+                conv_next = conv_l
+                for conv, xin, y, z, bn in reversed(units):
+                    self.dgrad_into(B, dz, conv_next, y)
+                    dz = self.conv_unit_backward(B, self.gbuf(y), y, z, bn, conv, xin)
+                    conv_next = conv
+                self.dgrad_into(B, dz, conv_next, x)
+                if blk.downsample is not None:
+                    dzd = self.conv_unit_backward(B, d_out, out, zd, bnd, dconv, x)
+                    self.dgrad_into(B, dzd, dconv, x)
+            self._bwd_builders.append(build_block)
+        return out
+
+    def _decoder(self, x1, skip, block, pool_input=False):
+        """DecoderBlockV2: relu(conv3x3(cat[x1, skip]) + b) -> relu(convT4x4s2(.) + b)   (src/unet_models.py:136-141)"""
+        net = self.net
+        F = self.fwd_ops
+        conv, deconv = block.block[0].conv, block.block[1]
+        n, h, w, c1 = x1.shape
+        cmid, cout = conv.out_channels, deconv.out_channels
+        w16 = net._packed(conv.weight, net._w16)
+        b1 = net._vec(conv.bias, net._p32)
+        wt16 = net._packed(deconv.weight, net._w16)
+        b2 = net._vec(deconv.bias, net._p32)
+        mid = self.act(n, h, w, cmid)
+        out = self.act(n, 2 * h, 2 * w, cout)
+        F.append(lambda: ops.conv_fwd(x1, w16, 3, 1, bias=b1, relu=True, x2=skip, out=mid))
+        F.append(lambda: ops.convt_fwd(mid, wt16, bias=b2, relu=True, out=out))
+        if self.training:
+            def build_dec(B):
+                g_out = self.gbuf(out)   # already masked by out's ReLU (the consumer's dgrad epilogue did it)
+                g_mid = self.gbuf(mid)
+                gwt = net._packed(deconv.weight, net._g32)
+                gb2 = net._vec(deconv.bias, net._g32)
+                gw = net._packed(conv.weight, net._g32)
+                gb1 = net._vec(conv.bias, net._g32)
+                B.append(lambda: ops.channel_sum(g_out, gb2))
+                B.append(lambda: ops.convt_wgrad(g_out, mid, gwt))
+                B.append(lambda: ops.convt_dgrad(g_out, wt16, relu_mask=mid, out=g_mid))
+                B.append(lambda: ops.channel_sum(g_mid, gb1))
+                B.append(lambda: ops.conv_wgrad(g_mid, x1, gw, 3, 1, ci_off=0))
+                if skip is not None:
+                    B.append(lambda: ops.conv_wgrad(g_mid, skip, gw, 3, 1, ci_off=c1))
+                # x1 is a decoder ReLU output (mask in the epilogue) unless it is the centre's max-pool output
+                self.dgrad_into(B, g_mid, conv, x1, relu_mask=None if pool_input else x1, ci_off=0)
+                if skip is not None:
+                    self.dgrad_into(B, g_mid, conv, skip, relu_mask=None, ci_off=c1)
+            self._bwd_builders.append(build_dec)
+        return out
+
+    # ------------------------------------------------------------------------------------------ execution
+    def _run_fwd(self):
+        if self.training:
+            self._stats_arena.zero_()
+        for op in self.fwd_ops:
+            op()
+
+    def _run_bwd(self):
+        self.net._g32.zero_()
+        for layer in self.bwd_layers:  # already in execution (reverse-forward) order
+            for op in layer:
+                op()
+
+    def forward(self, x, use_graph=True):
+        self.x_in.copy_(x)
+        if not use_graph:
+            self._run_fwd()
+            return self.logits
+        if self.graph_fwd is None:
+            self._run_fwd()  # eager warm-up (sets kernel attributes, validates arguments)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_fwd()
+            self.graph_fwd = g
+            return self.logits
+        self.graph_fwd.replay()
+        return self.logits
+
+    def backward(self, dlogits, use_graph=True):
+        self.dlogits.copy_(dlogits)
+        if not use_graph:
+            self._run_bwd()
+            return
+        if self.graph_bwd is None:
+            self._run_bwd()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_bwd()
+            self.graph_bwd = g
+            return
+        self.graph_bwd.replay()
+
+
+BN_MOMENTUM = 0.1
+BN_EPS = 1e-5
+
+
+class UNetFunction(torch.autograd.Function):
+    """autograd bridge: logits = UNet(x); backward fills the gradient arena and hands its views to the parameters"""
+
+    @staticmethod
+    def forward(ctx, x, net, plan, *params):
+        net.refresh_operands()
+        logits = plan.forward(x)
+        ctx.net, ctx.plan = net, plan
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net, plan = ctx.net, ctx.plan
+        plan.backward(dlogits.contiguous())
+        for p, gview in net.grad_views():
+            if p.grad is None:
+                p.grad = gview
+            elif p.grad.data_ptr() != gview.data_ptr():
+                p.grad.add_(gview)
+        return (None, None, None) + tuple(None for _ in ctx.needs_input_grad[3:])

@@ -134,3 +134,158 @@ def convt_wgrad(dy, x, dw):
     a.cout = dw.shape[1]; a.dw = dw.data_ptr()
     L.call("mcb_convt_wgrad", a)
     return dw
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HBM-bound glue
+# ---------------------------------------------------------------------------------------------------------------------
+F32 = torch.float32
+
+
+def nchw_to_nhwc_bf16(x, out=None):
+    _chk(x, F32)
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    L.fcall("mcb_nchw_f32_to_nhwc_bf16", x.data_ptr(), out.data_ptr(), n, c, h, w)
+    return out
+
+
+def nhwc_to_nchw_f32(x, out=None):
+    _chk(x)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=F32, device=x.device)
+    L.fcall("mcb_nhwc_bf16_to_nchw_f32", x.data_ptr(), out.data_ptr(), n, c, h, w)
+    return out
+
+
+def stem_im2col(x, out=None):
+    _chk(x, F32)
+    n, c, h, w = x.shape
+    assert c == 3
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, 192), dtype=torch.bfloat16, device=x.device)
+    L.fcall("mcb_stem_im2col", x.data_ptr(), out.data_ptr(), n, h, w)
+    return out
+
+
+def stem_pack_weight(w49x64x3, out):
+    L.fcall("mcb_stem_pack_weight", _chk(w49x64x3, F32).data_ptr(), _chk(out).data_ptr())
+    return out
+
+
+def stem_unpack_wgrad(dwp, dw):
+    L.fcall("mcb_stem_unpack_wgrad", _chk(dwp, F32).data_ptr(), _chk(dw, F32).data_ptr())
+
+
+def bn_finalize(stats, count, gamma, beta, rm, rv, scale, shift, mean, invstd, momentum=0.1, eps=1e-5):
+    c = gamma.numel()
+    L.fcall("mcb_bn_finalize", stats.data_ptr(), int(count), gamma.data_ptr(), beta.data_ptr(), L.dp(rm), L.dp(rv),
+            momentum, eps, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), c)
+
+
+def bn_eval_params(gamma, beta, rm, rv, scale, shift, eps=1e-5):
+    L.fcall("mcb_bn_eval_params", gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), eps,
+            scale.data_ptr(), shift.data_ptr(), gamma.numel())
+
+
+def bn_apply(z, scale, shift, out, relu=True, residual=None, res_scale=None, res_shift=None):
+    _chk(z); _chk(out)
+    c = z.shape[-1]
+    L.fcall("mcb_bn_apply", z.data_ptr(), scale.data_ptr(), shift.data_ptr(), L.dp(residual), L.dp(res_scale),
+            L.dp(res_shift), int(relu), out.data_ptr(), z.numel() // c, c)
+    return out
+
+
+def bn_bwd_reduce(dy, y_mask, z, mean, invstd, dbeta, dgamma):
+    c = z.shape[-1]
+    L.fcall("mcb_bn_bwd_reduce", _chk(dy).data_ptr(), L.dp(y_mask), _chk(z).data_ptr(), mean.data_ptr(),
+            invstd.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), z.numel() // c, c)
+
+
+def bn_bwd_apply(dy, y_mask, z, mean, invstd, gamma, dbeta, dgamma, dz, g_out=None, g_accumulate=False):
+    c = z.shape[-1]
+    L.fcall("mcb_bn_bwd_apply", _chk(dy).data_ptr(), L.dp(y_mask), _chk(z).data_ptr(), mean.data_ptr(),
+            invstd.data_ptr(), gamma.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), _chk(dz).data_ptr(), L.dp(g_out),
+            int(g_accumulate), z.numel() // c, c)
+
+
+def channel_sum(x, out):
+    c = x.shape[-1]
+    L.fcall("mcb_channel_sum", _chk(x).data_ptr(), out.data_ptr(), x.numel() // c, c)
+
+
+def maxpool2_fwd(x, out=None):
+    _chk(x)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    L.fcall("mcb_maxpool2_fwd", x.data_ptr(), out.data_ptr(), n, h, w, c)
+    return out
+
+
+def maxpool2_bwd(x, dy, dx, accumulate=False):
+    n, h, w, c = x.shape
+    L.fcall("mcb_maxpool2_bwd", _chk(x).data_ptr(), _chk(dy).data_ptr(), _chk(dx).data_ptr(), int(accumulate), n, h, w, c)
+    return dx
+
+
+def final_conv_fwd(x, w, b, logits):
+    n, h, wd, c = x.shape
+    k = b.numel()
+    L.fcall("mcb_final_conv_fwd", _chk(x).data_ptr(), w.data_ptr(), b.data_ptr(), _chk(logits, F32).data_ptr(), n, h,
+            wd, c, k)
+    return logits
+
+
+def final_conv_bwd(x, w, dlogits, dx, dw, db):
+    n, h, wd, c = x.shape
+    k = db.numel()
+    L.fcall("mcb_final_conv_bwd", _chk(x).data_ptr(), w.data_ptr(), _chk(dlogits, F32).data_ptr(), _chk(dx).data_ptr(),
+            dw.data_ptr(), db.data_ptr(), n, h, wd, c, k)
+
+
+def adam_step(p, g, m, v, p_bf16, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    L.fcall("mcb_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), L.dp(p_bf16), p.numel(), lr,
+            betas[0], betas[1], eps, weight_decay, int(step), grad_scale)
+
+
+def cast_bf16(x, out):
+    L.fcall("mcb_cast_f32_bf16", _chk(x, F32).data_ptr(), _chk(out).data_ptr(), x.numel())
+    return out
+
+
+def _loss_args(logits, target, mode, cfg):
+    a = L.LossArgs()
+    n, k, h, w = logits.shape
+    assert k == 2, "the CUDA loss kernels implement the reference's 2-class configuration"
+    assert target.shape == (n, 3 if mode == 0 else 1, h, w), target.shape
+    a.logits = _chk(logits, F32).data_ptr(); a.target = _chk(target, F32).data_ptr()
+    a.n, a.h, a.w, a.mode = n, h, w, mode
+    a.w0 = cfg.get("w0", 50.0); a.sigma = cfg.get("sigma", 10.0); a.size_c = cfg.get("size_c", 128.0)
+    a.dice_weight = cfg.get("dice_weight", 0.2); a.ce_weight = cfg.get("ce_weight", 1.0)
+    a.dice_smooth = cfg.get("dice_smooth", 1.0)
+    return a
+
+
+def loss_partials(logits, target, sums, mode=0, **cfg):
+    """sums: float64[4] on device, zeroed by the caller; += (sum p1*t, sum p1, sum t, sum w*ce)"""
+    a = _loss_args(logits, target, mode, cfg)
+    L.fcall("mcb_loss_partials", C.byref(a), sums.data_ptr())
+
+
+def loss_grad(logits, target, sums, dlogits, loss_out, global_pixels=None, grad_scale=1.0, mode=0, **cfg):
+    a = _loss_args(logits, target, mode, cfg)
+    n, _, h, w = logits.shape
+    L.fcall("mcb_loss_grad", C.byref(a), sums.data_ptr(), int(global_pixels or n * h * w), grad_scale,
+            dlogits.data_ptr(), L.dp(loss_out))
+
+
+def softmax2(logits, out=None):
+    n, k, h, w = logits.shape
+    assert k == 2
+    if out is None:
+        out = torch.empty_like(logits)
+    L.fcall("mcb_softmax2", _chk(logits, F32).data_ptr(), out.data_ptr(), n, h, w)
+    return out
