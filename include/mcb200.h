@@ -182,6 +182,36 @@ int mcb_loss_grad(const mcb_loss_args* a, const double* sums, long global_pixels
 /* numpy softmax over the class axis (src/utils.py:231-273 at src/models.py:88-92) */
 int mcb_softmax2(const float* logits, float* probs, int n, int h, int w, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-pixel mask post-processing (src/postprocessing.py:48-258, src/utils.py:328-339), batched: a "plane" is one
+ * (image, layer) 2-D map; all planes of a batch are processed by one call.  Integer / bool outputs and the float64
+ * resize are bit-exact against the reference path (scipy.ndimage / skimage as restated in oracle/post_oracle.py).
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* resize_image (src/postprocessing.py:48-61) -> skimage.transform.resize(mode='constant'), n-D branch:
+ * x fp32 [n][c][hi][wi] -> y fp64 [n][c][ho][wo]; minmax_ws: fp32 [2*n] scratch */
+int mcb_resize_bilinear_f64(const float* x, double* y, float* minmax_ws, int n, int c, int hi, int wi, int ho, int wo,
+                            void* stream);
+/* categorize_multilayer_image (src/postprocessing.py:77-84): out uint8 [n][layers][h][w] = prob[layer_channel[l]] >
+ * thresholds[l]; prob fp32 or fp64 [n][c][h][w] */
+int mcb_threshold_layers(const void* prob, int prob_is_f64, const double* thresholds, const int* layer_channel,
+                         uint8_t* out, int n, int c, int layers, int h, int w, void* stream);
+/* label / label_multilayer_image (src/utils.py:328-330, src/postprocessing.py:127-132) -> scipy.ndimage.label:
+ * 4-connectivity, labels 1..K in raster order of each component's first pixel, int32.
+ * mask uint8 or int32 [planes][h][w]; workspace int32 [planes*h*w]; counts int32 [planes] (K per plane) or NULL */
+int mcb_ccl_label(const void* mask, int mask_is_i32, int* labels, int* workspace, int* counts, int planes, int h, int w,
+                  void* stream);
+/* skimage.morphology.erosion / dilation with rectangle(size, size) (src/postprocessing.py:135-180): uint8 or int32 */
+int mcb_morph_rect(const void* in, void* out, int is_i32, int is_dilation, int size, int planes, int h, int w,
+                   void* stream);
+/* add_dropped_objects (src/utils.py:333-339), per 2-D plane; workspace int32 [2*planes*h*w] */
+int mcb_add_dropped_objects(const uint8_t* original, const uint8_t* processed, uint8_t* out, int* workspace, int planes,
+                            int h, int w, void* stream);
+/* build_score (src/postprocessing.py:228-236): scores[offsets[p] + l - 1] = mean(prob[labels == l]) * sqrt(area);
+ * offsets int32 [planes] (exclusive prefix of the per-plane label counts); sums/counts/scores sized total_instances */
+int mcb_instance_scores(const int* labels, const void* prob, int prob_is_f64, const int* offsets, double* sums,
+                        int* counts, double* scores, int total_instances, int planes, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

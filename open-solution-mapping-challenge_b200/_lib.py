@@ -116,3 +116,15 @@ def fcall(name, *args):
     import torch
     rc = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
     check(rc, name)
+
+_SIGS2 = {
+    "mcb_resize_bilinear_f64": [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    "mcb_threshold_layers": [vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "mcb_ccl_label": [vp, ci, vp, vp, vp, ci, ci, ci, vp],
+    "mcb_morph_rect": [vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    "mcb_add_dropped_objects": [vp, vp, vp, vp, ci, ci, ci, vp],
+    "mcb_instance_scores": [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp],
+}
+for _n, _a in _SIGS2.items():
+    getattr(lib, _n).argtypes = _a
+    getattr(lib, _n).restype = ci

@@ -16,6 +16,28 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+class _Op:
+    """one launch (or a tiny group) with its algorithmic cost, for the per-kernel breakdown in bench.py"""
+    __slots__ = ("kind", "fn", "flops", "bytes")
+
+    def __init__(self, kind, fn, flops=0.0, nbytes=0.0):
+        self.kind, self.fn, self.flops, self.bytes = kind, fn, float(flops), float(nbytes)
+
+    def __call__(self):
+        return self.fn()
+
+
+def _nb(*tensors):
+    return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
+
+
+class _OpList(list):
+    """list of _Op; .add(kind, fn, flops, bytes)"""
+
+    def add(self, kind, fn, flops=0.0, nbytes=0.0):
+        self.append(_Op(kind, fn, flops, nbytes))
+
+
 class _BN:
     """per-BatchNorm device state"""
     __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta")
@@ -25,7 +47,7 @@ class Plan:
     def __init__(self, net, n, h, w, training):
         self.net, self.n, self.h, self.w, self.training = net, n, h, w, training
         self.dev = net._p32.device
-        self.fwd_ops = []          # closures, in order
+        self.fwd_ops = _OpList()   # _Op launches, in order
         self.bwd_layers = []       # list of lists of closures (one list per forward unit), executed in reverse
         self.grad = {}             # id(activation) -> gradient buffer
         self.written = set()       # gradient buffers that already hold a contribution
@@ -41,7 +63,7 @@ class Plan:
         self.logits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
         self._build()
         for builder in reversed(self._bwd_builders):
-            B = []
+            B = _OpList()
             builder(B)
             self.bwd_layers.append(B)
         self.launches_fwd = len(self.fwd_ops)
@@ -94,23 +116,26 @@ class Plan:
         bn = self.bn_state(bnmod)
         w16 = net._packed(conv.weight, net._w16)
         F = self.fwd_ops
+        cflops = 2.0 * z.numel() * cin * k * k
         if self.training:
-            F.append(lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z))
+            F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z), cflops, _nb(x, w16, z))
             cnt = z.numel() // cout
-            F.append(lambda: ops.bn_finalize(bn.stats, cnt, bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var,
-                                             bn.scale, bn.shift, bn.mean, bn.invstd, BN_MOMENTUM, BN_EPS))
+            F.add("bn_finalize", lambda: ops.bn_finalize(bn.stats, cnt, bn.gamma, bn.beta, bnmod.running_mean,
+                                                        bnmod.running_var, bn.scale, bn.shift, bn.mean, bn.invstd,
+                                                        BN_MOMENTUM, BN_EPS))
         else:
-            F.append(lambda: ops.conv_fwd(x, w16, k, s, out=z))
-            F.append(lambda: ops.bn_eval_params(bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var, bn.scale,
-                                                bn.shift, BN_EPS))
+            F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, out=z), cflops, _nb(x, w16, z))
+            F.add("bn_finalize", lambda: ops.bn_eval_params(bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var,
+                                                           bn.scale, bn.shift, BN_EPS))
         if relu is None:
             return None, z, bn
         y = out if out is not None else self.act(*z.shape)
         if res_bn is not None:
             rb = res_bn
-            F.append(lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, rb.scale, rb.shift))
+            F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, rb.scale, rb.shift),
+                  0, _nb(z, y, residual))
         else:
-            F.append(lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual))
+            F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual), 0, _nb(z, y, residual))
         return y, z, bn
 
     def conv_unit_backward(self, B, dy, ymask, z, bn, conv, x, g_out=None, g_out_acc=False):
@@ -121,10 +146,12 @@ class Plan:
         dz = self.act(*z.shape)
         w16 = net._packed(conv.weight, net._w16)
         gw = net._packed(conv.weight, net._g32)
-        B.append(lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma))
-        B.append(lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma, dz, g_out,
-                                          g_out_acc))
-        B.append(lambda: ops.conv_wgrad(dz, x, gw, k, s))
+        B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma), 0,
+              _nb(dy, ymask, z))
+        B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma,
+                                                      dz, g_out, g_out_acc), 0, _nb(dy, ymask, z, dz, g_out))
+        B.add("conv_wgrad", lambda: ops.conv_wgrad(dz, x, gw, k, s), 2.0 * dz.numel() * x.shape[3] * k * k,
+              _nb(dz, x, gw))
         return dz
 
     def dgrad_into(self, B, dz, conv, x, relu_mask=None, ci_off=0):
@@ -138,8 +165,9 @@ class Plan:
         cin = x.shape[3]
         if acc and relu_mask is not None:
             raise RuntimeError("plan error: masked dgrad cannot accumulate")
-        B.append(lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
-                                        accumulate=acc, out=gx))
+        B.add("conv_dgrad", lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
+                                                   accumulate=acc, out=gx), 2.0 * dz.numel() * cin * k * k,
+              _nb(dz, gx, relu_mask) + (_nb(gx) if acc else 0) + 2.0 * k * k * dz.shape[3] * cin)
 
     # ------------------------------------------------------------------------------------------ network
     def _build(self):
@@ -153,24 +181,25 @@ class Plan:
         stem_w16 = torch.zeros((1, 64, 192), dtype=BF16, device=self.dev)
         self._keep.append(stem_w16)
         stem_master = net._vec(enc.conv1.weight, net._p32)
-        F.append(lambda: ops.stem_im2col(self.x_in, col))
-        F.append(lambda: ops.stem_pack_weight(stem_master, stem_w16))
+        F.add("stem_im2col", lambda: ops.stem_im2col(self.x_in, col), 0, _nb(self.x_in, col))
+        F.add("misc", lambda: ops.stem_pack_weight(stem_master, stem_w16))
+        sflops = 2.0 * n * (h // 2) * (w // 2) * 64 * 147
         z0 = self.act(n, h // 2, w // 2, 64)
         bn0 = self.bn_state(enc.bn1)
         if train:
-            F.append(lambda: ops.conv_fwd(col, stem_w16, 1, 1, stats=bn0.stats, out=z0))
+            F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, stats=bn0.stats, out=z0), sflops, _nb(col, z0))
             cnt0 = z0.numel() // 64
-            F.append(lambda: ops.bn_finalize(bn0.stats, cnt0, bn0.gamma, bn0.beta, enc.bn1.running_mean,
-                                             enc.bn1.running_var, bn0.scale, bn0.shift, bn0.mean, bn0.invstd,
-                                             BN_MOMENTUM, BN_EPS))
+            F.add("bn_finalize", lambda: ops.bn_finalize(bn0.stats, cnt0, bn0.gamma, bn0.beta, enc.bn1.running_mean,
+                                                        enc.bn1.running_var, bn0.scale, bn0.shift, bn0.mean,
+                                                        bn0.invstd, BN_MOMENTUM, BN_EPS))
         else:
-            F.append(lambda: ops.conv_fwd(col, stem_w16, 1, 1, out=z0))
-            F.append(lambda: ops.bn_eval_params(bn0.gamma, bn0.beta, enc.bn1.running_mean, enc.bn1.running_var,
-                                                bn0.scale, bn0.shift, BN_EPS))
+            F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, out=z0), sflops, _nb(col, z0))
+            F.add("bn_finalize", lambda: ops.bn_eval_params(bn0.gamma, bn0.beta, enc.bn1.running_mean,
+                                                           enc.bn1.running_var, bn0.scale, bn0.shift, BN_EPS))
         a0 = self.act(*z0.shape)
-        F.append(lambda: ops.bn_apply(z0, bn0.scale, bn0.shift, a0, True))
+        F.add("bn_apply", lambda: ops.bn_apply(z0, bn0.scale, bn0.shift, a0, True), 0, _nb(z0, a0))
         c1 = self.act(n, h // 4, w // 4, 64)
-        F.append(lambda: ops.maxpool2_fwd(a0, c1))
+        F.add("maxpool", lambda: ops.maxpool2_fwd(a0, c1), 0, _nb(a0, c1))
         if train:
             def build_stem(B):
                 d_a0 = self.gbuf(a0)
@@ -179,13 +208,14 @@ class Plan:
                 stem_gw = torch.zeros((1, 64, 192), dtype=F32, device=self.dev)
                 self._keep.append(stem_gw)
                 stem_g = net._vec(enc.conv1.weight, net._g32)
-                B.append(lambda: ops.maxpool2_bwd(a0, d_c1, d_a0, False))
-                B.append(lambda: ops.bn_bwd_reduce(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.dbeta, bn0.dgamma))
-                B.append(lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma, bn0.dbeta,
-                                                  bn0.dgamma, dz0))
-                B.append(lambda: stem_gw.zero_())
-                B.append(lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1))
-                B.append(lambda: ops.stem_unpack_wgrad(stem_gw, stem_g))
+                B.add("maxpool", lambda: ops.maxpool2_bwd(a0, d_c1, d_a0, False), 0, _nb(a0, d_c1, d_a0))
+                B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.dbeta,
+                                                                bn0.dgamma), 0, _nb(d_a0, a0, z0))
+                B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma,
+                                                              bn0.dbeta, bn0.dgamma, dz0), 0, _nb(d_a0, a0, z0, dz0))
+                B.add("misc", lambda: stem_gw.zero_())
+                B.add("conv_wgrad", lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1), sflops, _nb(dz0, col))
+                B.add("misc", lambda: ops.stem_unpack_wgrad(stem_gw, stem_g))
             self._bwd_builders.append(build_stem)
 
         # ---- encoder stages (torchvision BasicBlock / Bottleneck)
@@ -199,12 +229,12 @@ class Plan:
 
         # ---- centre + decoder (src/unet_models.py:373-403)
         pool = self.act(n, c5.shape[1] // 2, c5.shape[2] // 2, c5.shape[3])
-        F.append(lambda: ops.maxpool2_fwd(c5, pool))
+        F.add("maxpool", lambda: ops.maxpool2_fwd(c5, pool), 0, _nb(c5, pool))
         if train:
             def build_pool(B):
                 d_pool, d_c5 = self.gbuf(pool), self.gbuf(c5)
                 acc = self.gmode(c5)  # dec5's skip dgrad ran first -> accumulate
-                B.append(lambda: ops.maxpool2_bwd(c5, d_pool, d_c5, acc))
+                B.add("maxpool", lambda: ops.maxpool2_bwd(c5, d_pool, d_c5, acc), 0, _nb(c5, d_pool, d_c5))
             self._bwd_builders.append(build_pool)
         center = self._decoder(pool, None, net.center, pool_input=True)
         d5 = self._decoder(center, c5, net.dec5)
@@ -217,9 +247,11 @@ class Plan:
         w0_16 = net._packed(conv0.weight, net._w16)
         b0 = net._vec(conv0.bias, net._p32)
         d0 = self.act(n, h, w, conv0.out_channels)
-        F.append(lambda: ops.conv_fwd(d1, w0_16, 3, 1, bias=b0, relu=True, out=d0))
+        f0 = 2.0 * d0.numel() * d1.shape[3] * 9
+        F.add("conv_fwd", lambda: ops.conv_fwd(d1, w0_16, 3, 1, bias=b0, relu=True, out=d0), f0, _nb(d1, d0))
         fw, fb = net._vec(net.final.weight, net._p32), net._vec(net.final.bias, net._p32)
-        F.append(lambda: ops.final_conv_fwd(d0, fw, fb, self.logits))
+        F.add("final_conv", lambda: ops.final_conv_fwd(d0, fw, fb, self.logits), 2.0 * self.logits.numel() * 32,
+              _nb(d0, self.logits))
         self.named = dict(conv1=c1, conv2=c2, conv3=c3, conv4=c4, conv5=c5, center=center, dec5=d5, dec4=d4, dec3=d3,
                           dec2=d2, dec1=d1, dec0=d0)
         if train:
@@ -227,11 +259,12 @@ class Plan:
                 g_d0 = self.gbuf(d0)
                 gfw, gfb = net._vec(net.final.weight, net._g32), net._vec(net.final.bias, net._g32)
                 # final 1x1 backward also applies dec0's ReLU mask
-                B.append(lambda: ops.final_conv_bwd(d0, fw, self.dlogits, g_d0, gfw, gfb))
+                B.add("final_conv", lambda: ops.final_conv_bwd(d0, fw, self.dlogits, g_d0, gfw, gfb),
+                      4.0 * self.logits.numel() * 32, _nb(d0, self.dlogits, g_d0))
                 gb0 = net._vec(conv0.bias, net._g32)
                 gw0 = net._packed(conv0.weight, net._g32)
-                B.append(lambda: ops.channel_sum(g_d0, gb0))
-                B.append(lambda: ops.conv_wgrad(g_d0, d1, gw0, 3, 1))
+                B.add("channel_sum", lambda: ops.channel_sum(g_d0, gb0), 0, _nb(g_d0))
+                B.add("conv_wgrad", lambda: ops.conv_wgrad(g_d0, d1, gw0, 3, 1), f0, _nb(g_d0, d1))
                 self.dgrad_into(B, g_d0, conv0, d1, relu_mask=d1)
             self._bwd_builders.append(build_head)
 
@@ -254,9 +287,10 @@ class Plan:
         if blk.downsample is not None:
             dconv, dbnm = blk.downsample[0], blk.downsample[1]
             _, zd, bnd = self.conv_bn(x, dconv, dbnm, None)
-            F.append(lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, zd, bnd.scale, bnd.shift))
+            F.add("bn_apply", lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, zd, bnd.scale, bnd.shift), 0,
+                  _nb(z_l, out, zd))
         else:
-            F.append(lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, x))
+            F.add("bn_apply", lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, x), 0, _nb(z_l, out, x))
         if train:
             last_in = cur
 
@@ -296,8 +330,12 @@ class Plan:
         b2 = net._vec(deconv.bias, net._p32)
         mid = self.act(n, h, w, cmid)
         out = self.act(n, 2 * h, 2 * w, cout)
-        F.append(lambda: ops.conv_fwd(x1, w16, 3, 1, bias=b1, relu=True, x2=skip, out=mid))
-        F.append(lambda: ops.convt_fwd(mid, wt16, bias=b2, relu=True, out=out))
+        ctot = c1 + (skip.shape[3] if skip is not None else 0)
+        fc = 2.0 * mid.numel() * ctot * 9
+        ft = 2.0 * mid.numel() * cout * 16
+        F.add("conv_fwd", lambda: ops.conv_fwd(x1, w16, 3, 1, bias=b1, relu=True, x2=skip, out=mid), fc,
+              _nb(x1, skip, w16, mid))
+        F.add("convt_fwd", lambda: ops.convt_fwd(mid, wt16, bias=b2, relu=True, out=out), ft, _nb(mid, wt16, out))
         if self.training:
             def build_dec(B):
                 g_out = self.gbuf(out)   # already masked by out's ReLU (the consumer's dgrad epilogue did it)
@@ -306,13 +344,16 @@ class Plan:
                 gb2 = net._vec(deconv.bias, net._g32)
                 gw = net._packed(conv.weight, net._g32)
                 gb1 = net._vec(conv.bias, net._g32)
-                B.append(lambda: ops.channel_sum(g_out, gb2))
-                B.append(lambda: ops.convt_wgrad(g_out, mid, gwt))
-                B.append(lambda: ops.convt_dgrad(g_out, wt16, relu_mask=mid, out=g_mid))
-                B.append(lambda: ops.channel_sum(g_mid, gb1))
-                B.append(lambda: ops.conv_wgrad(g_mid, x1, gw, 3, 1, ci_off=0))
+                B.add("channel_sum", lambda: ops.channel_sum(g_out, gb2), 0, _nb(g_out))
+                B.add("convt_wgrad", lambda: ops.convt_wgrad(g_out, mid, gwt), ft, _nb(g_out, mid, gwt))
+                B.add("convt_dgrad", lambda: ops.convt_dgrad(g_out, wt16, relu_mask=mid, out=g_mid), ft,
+                      _nb(g_out, wt16, mid, g_mid))
+                B.add("channel_sum", lambda: ops.channel_sum(g_mid, gb1), 0, _nb(g_mid))
+                B.add("conv_wgrad", lambda: ops.conv_wgrad(g_mid, x1, gw, 3, 1, ci_off=0),
+                      2.0 * mid.numel() * c1 * 9, _nb(g_mid, x1))
                 if skip is not None:
-                    B.append(lambda: ops.conv_wgrad(g_mid, skip, gw, 3, 1, ci_off=c1))
+                    B.add("conv_wgrad", lambda: ops.conv_wgrad(g_mid, skip, gw, 3, 1, ci_off=c1),
+                          2.0 * mid.numel() * skip.shape[3] * 9, _nb(g_mid, skip))
                 # x1 is a decoder ReLU output (mask in the epilogue) unless it is the centre's max-pool output
                 self.dgrad_into(B, g_mid, conv, x1, relu_mask=None if pool_input else x1, ci_off=0)
                 if skip is not None:

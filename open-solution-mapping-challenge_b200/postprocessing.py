@@ -1,0 +1,271 @@
+"""Mirror of the reference's per-pixel post-processing (/root/reference/src/postprocessing.py:48-258,
+/root/reference/src/utils.py:231-273,328-339) on the GPU.
+
+Two surfaces:
+  * module-level functions with the reference's names and signatures, one image in / numpy out — drop-ins for
+    `make_apply_transformer(post.<fn>, ...)` in src/pipelines.py:248-304 (each call round-trips the image over PCIe);
+  * `MaskPostprocessor`, the batched transformer the fast path uses: the whole batch of probability maps stays on the
+    device through resize/crop -> threshold -> erode -> label -> dilate -> score, one launch sequence per batch.
+
+All arithmetic is in libmcb200.so (csrc/postproc.cu); torch only owns the device buffers.  No CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+
+CATEGORY_LAYERS = [1, 1]  # src/pipeline_config.py:18
+MEAN = [0.485, 0.456, 0.406]
+STD = [0.229, 0.224, 0.225]
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mcb200.postprocessing needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_dev(a, dtype):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=_dev(), dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=_dev(), dtype=dtype)
+
+
+def layer_thresholds(category_layers=None):
+    """threshold list and source channel of every output layer (src/postprocessing.py:77-84)"""
+    category_layers = CATEGORY_LAYERS if category_layers is None else category_layers
+    thr, chan = [], []
+    for c, n_layers in enumerate(category_layers):
+        step = 1. / (n_layers + 1)
+        for t in np.arange(step, 1, step):
+            thr.append(float(t))
+            chan.append(c)
+    return thr, chan
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device-level batched primitives (tensors in, tensors out; leading dims are planes / images)
+# ---------------------------------------------------------------------------------------------------------------------
+def resize_batch(probs, target_size):
+    """probs (N, C, Hi, Wi) float32 cuda -> (N, C, Ho, Wo) float64 cuda"""
+    assert probs.dtype == torch.float32 and probs.is_cuda and probs.is_contiguous()
+    n, c, hi, wi = probs.shape
+    ho, wo = int(target_size[0]), int(target_size[1])
+    out = torch.empty((n, c, ho, wo), dtype=torch.float64, device=probs.device)
+    ws = torch.empty(2 * n, dtype=torch.float32, device=probs.device)
+    L.fcall("mcb_resize_bilinear_f64", probs.data_ptr(), out.data_ptr(), ws.data_ptr(), n, c, hi, wi, ho, wo)
+    return out
+
+
+def threshold_batch(probs, category_layers=None):
+    """probs (N, C, H, W) float32|float64 cuda -> (N, L, H, W) uint8 (0/1)"""
+    assert probs.is_cuda and probs.is_contiguous() and probs.dtype in (torch.float32, torch.float64)
+    n, c, h, w = probs.shape
+    thr, chan = layer_thresholds(category_layers)
+    assert len(category_layers or CATEGORY_LAYERS) <= c or max(chan) < c
+    t = torch.tensor(thr, dtype=torch.float64, device=probs.device)
+    ch = torch.tensor(chan, dtype=torch.int32, device=probs.device)
+    out = torch.empty((n, len(thr), h, w), dtype=torch.uint8, device=probs.device)
+    L.fcall("mcb_threshold_layers", probs.data_ptr(), int(probs.dtype == torch.float64), t.data_ptr(), ch.data_ptr(),
+            out.data_ptr(), n, c, len(thr), h, w)
+    return out
+
+
+def label_batch(mask, return_counts=False):
+    """mask (..., H, W) uint8|int32 cuda -> int32 labels, same shape (scipy.ndimage.label numbering per plane)"""
+    assert mask.is_cuda and mask.is_contiguous() and mask.dtype in (torch.uint8, torch.int32, torch.bool)
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    h, w = mask.shape[-2:]
+    planes = mask.numel() // (h * w)
+    labels = torch.empty(mask.shape, dtype=torch.int32, device=mask.device)
+    ws = torch.empty(mask.numel(), dtype=torch.int32, device=mask.device)
+    counts = torch.empty(planes, dtype=torch.int32, device=mask.device)
+    L.fcall("mcb_ccl_label", mask.data_ptr(), int(mask.dtype == torch.int32), labels.data_ptr(), ws.data_ptr(),
+            counts.data_ptr(), planes, h, w)
+    return (labels, counts) if return_counts else labels
+
+
+def morph_batch(x, size, dilation):
+    """skimage erosion / dilation with rectangle(size, size) per plane; x (..., H, W) uint8|int32 cuda"""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (torch.uint8, torch.int32)
+    h, w = x.shape[-2:]
+    out = torch.empty_like(x)
+    L.fcall("mcb_morph_rect", x.data_ptr(), out.data_ptr(), int(x.dtype == torch.int32), int(dilation), int(size),
+            x.numel() // (h * w), h, w)
+    return out
+
+
+def erode_batch(mask, size):
+    """erode_image per plane incl. add_dropped_objects (src/postprocessing.py:135-156); mask uint8 -> uint8"""
+    if not size > 0:
+        return mask
+    assert mask.dtype == torch.uint8
+    h, w = mask.shape[-2:]
+    planes = mask.numel() // (h * w)
+    eroded = morph_batch(mask, size, dilation=False)
+    out = torch.empty_like(mask)
+    ws = torch.empty(2 * mask.numel(), dtype=torch.int32, device=mask.device)
+    L.fcall("mcb_add_dropped_objects", mask.data_ptr(), eroded.data_ptr(), out.data_ptr(), ws.data_ptr(), planes, h, w)
+    return out
+
+
+def scores_batch(labels, probs, counts):
+    """labels (P, H, W) int32, probs (P, H, W) float32|float64, counts (P,) int32 (max label per plane)
+    -> (scores float64 (sum counts,), offsets (P,) numpy) ; empty instances score NaN"""
+    assert labels.is_cuda and labels.is_contiguous() and probs.is_contiguous()
+    p, h, w = labels.shape
+    counts_h = counts.cpu().numpy().astype(np.int64)
+    offsets_h = np.concatenate([[0], np.cumsum(counts_h)[:-1]]).astype(np.int32) if p else np.zeros(0, np.int32)
+    total = int(counts_h.sum())
+    scores = torch.empty(max(total, 1), dtype=torch.float64, device=labels.device)
+    if total > 0:
+        offs = torch.from_numpy(offsets_h).to(labels.device)
+        sums = torch.empty(total, dtype=torch.float64, device=labels.device)
+        cnt = torch.empty(total, dtype=torch.int32, device=labels.device)
+        L.fcall("mcb_instance_scores", labels.data_ptr(), probs.data_ptr(), int(probs.dtype == torch.float64),
+                offs.data_ptr(), sums.data_ptr(), cnt.data_ptr(), scores.data_ptr(), total, p, h, w)
+    return scores[:total], offsets_h, counts_h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference-signature per-image functions (numpy in / numpy out)
+# ---------------------------------------------------------------------------------------------------------------------
+def softmax(X, theta=1.0, axis=None):
+    """src/utils.py:231-273 for the pipeline's use (2 classes along `axis` of an (N,2,H,W) or (2,H,W) array)"""
+    from . import ops
+    X = np.asarray(X)
+    if theta != 1.0 or X.ndim not in (3, 4) or (axis not in (0, 1)) or X.shape[axis] != 2 or (X.ndim == 3) != (axis == 0):
+        raise NotImplementedError("mcb200 softmax implements the pipeline's 2-class channel softmax only")
+    x4 = _to_dev(X if X.ndim == 4 else X[None], torch.float32)
+    out = ops.softmax2(x4).cpu().numpy()
+    return out if X.ndim == 4 else out[0]
+
+
+def resize_image(image, target_size):
+    x = _to_dev(image, torch.float32)
+    return resize_batch(x[None], target_size)[0].cpu().numpy()
+
+
+def categorize_image(image):
+    raise NotImplementedError("categorize_image (argmax) is only used by the validation callback; use "
+                              "categorize_multilayer_image")
+
+
+def categorize_multilayer_image(image):
+    image = np.asarray(image)
+    x = _to_dev(image, torch.float64 if image.dtype == np.float64 else torch.float32)
+    return threshold_batch(x[None])[0].cpu().numpy().astype(bool)
+
+
+def label_multiclass_image(mask):
+    mask = np.asarray(mask)
+    planes = np.stack([(mask == c) for c in range(0, mask.max() + 1)]).astype(np.uint8)
+    return label_batch(_to_dev(planes, torch.uint8)).cpu().numpy()
+
+
+def label_multilayer_image(mask):
+    m = np.asarray(mask)
+    return label_batch(_to_dev((m != 0).astype(np.uint8), torch.uint8)).cpu().numpy()
+
+
+def erode_image(mask, erode_selem_size):
+    if not erode_selem_size > 0:
+        return mask
+    m = _to_dev((np.asarray(mask) != 0).astype(np.uint8), torch.uint8)
+    return erode_batch(m, erode_selem_size).cpu().numpy()
+
+
+def dilate_image(mask, dilate_selem_size):
+    if not dilate_selem_size > 0:
+        return mask
+    m = np.asarray(mask)
+    if m.dtype == np.int32:
+        x = _to_dev(m, torch.int32)
+    elif m.dtype in (np.uint8, np.bool_):
+        x = _to_dev(m.astype(np.uint8), torch.uint8)
+    else:
+        raise NotImplementedError("dilate_image: dtype %s (the pipeline dilates int32 label maps)" % m.dtype)
+    out = morph_batch(x, dilate_selem_size, dilation=True).cpu().numpy()
+    return out.astype(bool) if m.dtype == np.bool_ else out
+
+
+def build_score(image, probabilities):
+    labels = _to_dev(np.asarray(image), torch.int32)
+    probs = np.asarray(probabilities)
+    p = min(labels.shape[0], probs.shape[0])  # zip() pairing of the reference
+    pr = _to_dev(probs[:p], torch.float64 if probs.dtype == np.float64 else torch.float32)
+    counts = labels[:p].reshape(p, -1).max(dim=1).values.to(torch.int32)
+    scores, offs, cnts = scores_batch(labels[:p].contiguous(), pr, counts)
+    s = scores.cpu().numpy()
+    total = []
+    for i in range(p):
+        vals = s[offs[i]:offs[i] + cnts[i]]
+        total.append([np.ma.masked if np.isnan(v) else v for v in vals])
+    return image, total
+
+
+def crop_image_center_per_class(image, h_crop, w_crop):
+    """src/postprocessing.py:239-258 — pure indexing"""
+    out = []
+    for class_prediction in image:
+        h, w = class_prediction.shape[:2]
+        h_start, w_start = int((h - h_crop) / 2.), int((w - w_crop) / 2.)
+        out.append(class_prediction[h_start:-h_start, w_start:-w_start])
+    return np.stack(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# batched transformer
+# ---------------------------------------------------------------------------------------------------------------------
+class MaskPostprocessor:
+    """mask_postprocessing of src/pipelines.py:248-304 for a whole batch on the device:
+    (resize | centre-crop) -> categorize_multilayer_image -> erode_image -> label_multilayer_image -> dilate_image
+    -> build_score.  transform() returns {'y_pred': [(labels (L,H,W) int32, [[score, ...], ...]), ...]} like the
+    reference's `output` step."""
+
+    def __init__(self, target_size=(300, 300), mode="resize", erode_selem_size=0, dilate_selem_size=0,
+                 category_layers=None):
+        assert mode in ("resize", "crop")
+        self.target_size, self.mode = tuple(target_size), mode
+        self.erode, self.dilate = erode_selem_size, dilate_selem_size
+        self.category_layers = category_layers or CATEGORY_LAYERS
+
+    def run_device(self, probs):
+        """probs (N, C, S, S) float32 cuda -> (labels int32 (N,L,H,W), scores float64, offsets, counts, probs_used)"""
+        assert probs.is_cuda and probs.dtype == torch.float32
+        probs = probs.contiguous()
+        if self.mode == "resize":
+            pr = resize_batch(probs, self.target_size)
+        else:
+            h, w = probs.shape[-2:]
+            h0, w0 = int((h - self.target_size[0]) / 2.), int((w - self.target_size[1]) / 2.)
+            pr = probs[:, :, h0:h - h0, w0:w - w0].contiguous()
+        masks = threshold_batch(pr, self.category_layers)
+        masks = erode_batch(masks, self.erode)
+        labels, counts = label_batch(masks, return_counts=True)
+        if self.dilate > 0:
+            labels = morph_batch(labels, self.dilate, dilation=True)
+        n, l, h, w = labels.shape
+        p = min(l, pr.shape[1])
+        if p != l or p != pr.shape[1]:
+            raise NotImplementedError("score pairing needs as many layers as probability channels (CATEGORY_LAYERS=[1,1])")
+        scores, offs, cnts = scores_batch(labels.view(n * l, h, w), pr.view(n * l, h, w), counts)
+        return labels, scores, offs, cnts, pr
+
+    def transform(self, images, **_):
+        probs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.stack(images)))
+        probs = probs.to(device=_dev(), dtype=torch.float32)
+        labels, scores, offs, cnts, _pr = self.run_device(probs)
+        lab = labels.cpu().numpy()
+        s = scores.cpu().numpy()
+        n, l = lab.shape[:2]
+        out = []
+        for i in range(n):
+            sc = []
+            for j in range(l):
+                pidx = i * l + j
+                vals = s[offs[pidx]:offs[pidx] + cnts[pidx]]
+                sc.append([np.ma.masked if np.isnan(v) else v for v in vals])
+            out.append((lab[i], sc))
+        return {"y_pred": out}

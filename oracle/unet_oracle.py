@@ -70,15 +70,52 @@ def make_reference_like_state_dict(encoder_depth, num_classes=2, num_filters=32,
     return sd
 
 
+class _RoundBF16(torch.autograd.Function):
+    """bf16 storage point: value rounded in forward, gradient rounded in backward (the CUDA path stores both
+    activations and activation gradients as bf16)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+class _RoundWeightBF16(torch.autograd.Function):
+    """bf16 operand copy of an fp32 master weight: rounded in forward, gradient passes through in fp32"""
+
+    @staticmethod
+    def forward(ctx, w):
+        return w.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class UNetOracle:
     """Functional forward over a state_dict.  training=True uses batch statistics and (optionally) updates the
-    running statistics in `sd` in place, exactly like nn.BatchNorm2d."""
+    running statistics in `sd` in place, exactly like nn.BatchNorm2d.
 
-    def __init__(self, sd, encoder_depth, update_running_stats=True):
+    emulate_bf16=True inserts the CUDA path's storage roundings (bf16 conv operands, bf16-stored conv outputs,
+    activations and activation gradients; fp32 accumulation, statistics, parameters and logits) so that the
+    product can be compared at tight tolerance; emulate_bf16=False is the reference's fp32 arithmetic."""
+
+    def __init__(self, sd, encoder_depth, update_running_stats=True, emulate_bf16=False):
         self.sd = strip_module_prefix(sd)
         self.depth = encoder_depth
         self.kind, self.blocks = LAYERS[encoder_depth]
         self.update = update_running_stats
+        self.emu = emulate_bf16
+
+    def _r(self, x):
+        return _RoundBF16.apply(x) if self.emu else x
+
+    def _w(self, key):
+        w = self.sd[key]
+        return _RoundWeightBF16.apply(w) if self.emu else w
 
     def _bn(self, x, prefix, training):
         sd = self.sd
@@ -93,22 +130,23 @@ class UNetOracle:
     def _block(self, x, p, stride, training):
         sd = self.sd
         identity = x
+        r, w = self._r, self._w
         if self.kind == "basic":
-            out = F.conv2d(x, sd[p + ".conv1.weight"], None, stride, 1)
-            out = F.relu(self._bn(out, p + ".bn1", training))
-            out = F.conv2d(out, sd[p + ".conv2.weight"], None, 1, 1)
+            out = r(F.conv2d(x, w(p + ".conv1.weight"), None, stride, 1))
+            out = r(F.relu(self._bn(out, p + ".bn1", training)))
+            out = r(F.conv2d(out, w(p + ".conv2.weight"), None, 1, 1))
             out = self._bn(out, p + ".bn2", training)
         else:
-            out = F.conv2d(x, sd[p + ".conv1.weight"])
-            out = F.relu(self._bn(out, p + ".bn1", training))
-            out = F.conv2d(out, sd[p + ".conv2.weight"], None, stride, 1)
-            out = F.relu(self._bn(out, p + ".bn2", training))
-            out = F.conv2d(out, sd[p + ".conv3.weight"])
+            out = r(F.conv2d(x, w(p + ".conv1.weight")))
+            out = r(F.relu(self._bn(out, p + ".bn1", training)))
+            out = r(F.conv2d(out, w(p + ".conv2.weight"), None, stride, 1))
+            out = r(F.relu(self._bn(out, p + ".bn2", training)))
+            out = r(F.conv2d(out, w(p + ".conv3.weight")))
             out = self._bn(out, p + ".bn3", training)
         if (p + ".downsample.0.weight") in sd:
-            identity = F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride)
+            identity = r(F.conv2d(x, w(p + ".downsample.0.weight"), None, stride))
             identity = self._bn(identity, p + ".downsample.1", training)
-        return F.relu(out + identity)
+        return r(F.relu(out + identity))
 
     def _layer(self, x, idx, training):
         for b in range(self.blocks[idx - 1]):
@@ -118,14 +156,16 @@ class UNetOracle:
 
     def _decoder(self, x, name):
         sd = self.sd
-        x = F.relu(F.conv2d(x, sd[name + ".block.0.conv.weight"], sd[name + ".block.0.conv.bias"], 1, 1))
-        x = F.conv_transpose2d(x, sd[name + ".block.1.weight"], sd[name + ".block.1.bias"], stride=2, padding=1)
-        return F.relu(x)
+        r, w = self._r, self._w
+        x = r(F.relu(F.conv2d(x, w(name + ".block.0.conv.weight"), sd[name + ".block.0.conv.bias"], 1, 1)))
+        x = F.conv_transpose2d(x, w(name + ".block.1.weight"), sd[name + ".block.1.bias"], stride=2, padding=1)
+        return r(F.relu(x))
 
     def forward(self, x, training=False, return_intermediates=False):
         sd = self.sd
-        c1 = F.conv2d(x, sd["encoder.conv1.weight"], None, 2, 3)
-        c1 = F.relu(self._bn(c1, "encoder.bn1", training))
+        r, w = self._r, self._w
+        c1 = r(F.conv2d(r(x), w("encoder.conv1.weight"), None, 2, 3))
+        c1 = r(F.relu(self._bn(c1, "encoder.bn1", training)))
         c1 = F.max_pool2d(c1, 2, 2)  # src/unet_models.py:356,363 — NOT torchvision's 3x3/s2 max-pool
         c2 = self._layer(c1, 1, training)
         c3 = self._layer(c2, 2, training)
@@ -138,7 +178,7 @@ class UNetOracle:
         d3 = self._decoder(torch.cat([d4, c3], 1), "dec3")
         d2 = self._decoder(torch.cat([d3, c2], 1), "dec2")
         d1 = self._decoder(d2, "dec1")
-        d0 = F.relu(F.conv2d(d1, sd["dec0.conv.weight"], sd["dec0.conv.bias"], 1, 1))
+        d0 = r(F.relu(F.conv2d(d1, w("dec0.conv.weight"), sd["dec0.conv.bias"], 1, 1)))
         logits = F.conv2d(d0, sd["final.weight"], sd["final.bias"])  # dropout2d(p=0) is the identity
         if return_intermediates:
             return logits, dict(conv1=c1, conv2=c2, conv3=c3, conv4=c4, conv5=c5, center=center, dec5=d5, dec4=d4,

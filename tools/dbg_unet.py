@@ -23,6 +23,7 @@ target[:, 2] = 1 + target[:, 0] * 15
 
 def rel(a, b):
     a, b = a.float().cpu(), b.float().cpu()
+    a, b = a.detach(), b.detach()
     return float((a - b).norm() / (b.norm() + 1e-12)), float((a - b).abs().max()), float(b.abs().max())
 
 
@@ -48,7 +49,9 @@ loss = O.mixed_loss(logits, target.to(dev), imsize=(S, S))
 loss.backward()
 torch.cuda.synchronize()
 print("first train step (eager + capture) %.2fs" % (time.time() - t0))
-oracle = O.UNetOracle(sd_o, depth)
+EMU = os.environ.get("EMU", "1") == "1"
+oracle = O.UNetOracle(sd_o, depth, emulate_bf16=EMU)
+print("oracle emulate_bf16 =", EMU)
 keys = O.trainable_keys(O.strip_module_prefix(sd_o))
 leaves = {k: sd_o[k].clone().requires_grad_(True) for k in keys}
 work = dict(sd_o); work.update(leaves)
@@ -69,6 +72,9 @@ for k, gref in zip(keys, grads):
     r = rel(p.grad, gref)
     cos = float(torch.nn.functional.cosine_similarity(p.grad.float().cpu().flatten(), gref.flatten(), dim=0))
     worst.append((r[0], cos, k, r[2]))
+print("all gradients in network order:")
+for r, cos, k, m in worst:
+    print("  %-45s rel %.4f cos %.4f refmax %.3g" % (k, r, cos, m))
 worst.sort(reverse=True)
 print("gradient check: %d tensors; median rel %.4f" % (len(worst), worst[len(worst) // 2][0]))
 for r, cos, k, m in worst[:12]:
