@@ -95,12 +95,29 @@ class ClockSampler:
         return out
 
 
+def usable_cores():
+    """host cores this process may actually use: affinity mask, cgroup CPU quota, capped at 32 (torch's intra-op
+    parallelism stops scaling — and on over-subscribed boxes collapses — beyond that for these layer sizes)"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def cpu_reference_arm(args, sample_batch=None, steps=None, warmup=None):
     """the reference's own CPU implementation of the train step (oracle port of Model._fit_loop, fp32, all host
     threads) on a bounded sample of the workload"""
     import torch
     from oracle import unet_oracle as O, synthetic
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     b = sample_batch or max(1, min(args.batch, 4))
     steps = steps or max(1, min(args.steps, 3))
@@ -109,8 +126,12 @@ def cpu_reference_arm(args, sample_batch=None, steps=None, warmup=None):
     x, t = synthetic.train_batch(b, args.size, seed=1234)
     X, T = torch.from_numpy(x), torch.from_numpy(t)
     opt = O.AdamOracle(lr=5e-4, weight_decay=1e-4)
+    tw = time.time()
     for _ in range(warmup):
         O.train_step(sd, args.encoder, X, T, opt, imsize=(256, 256))
+    tw = (time.time() - tw) / max(warmup, 1)
+    if warmup and tw * steps > 60:  # keep the whole arm bounded
+        steps = max(1, int(60 / tw))
     t0 = time.time()
     for _ in range(steps):
         O.train_step(sd, args.encoder, X, T, opt, imsize=(256, 256))
@@ -146,6 +167,14 @@ def breakdown(step, n_iter=2):
                 a[2] += o.flops
                 a[3] += o.bytes
     total = sum(a[1] for a in acc.values())
+    per_op = os.environ.get("MCB_BENCH_PER_OP")
+    if per_op:
+        rows = sorted(((e0.elapsed_time(e1), o) for o, e0, e1 in evs), key=lambda r: -r[0])
+        with open(per_op, "w") as f:
+            for ms, o in rows:
+                f.write("%8.4f ms  %-14s %-40s %7.1f TFLOP/s %8.1f GB/s\n" % (
+                    ms, o.kind, o.desc, o.flops / (ms * 1e-3) / 1e12 if ms > 0 else 0,
+                    o.bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0))
     out = {}
     for k, a in sorted(acc.items(), key=lambda kv: -kv[1][1]):
         out[k] = {"launches": a[0], "ms": round(a[1], 3), "share": round(a[1] / total, 4),
@@ -205,6 +234,13 @@ def main():
     from oracle import synthetic
 
     dev = torch.device("cuda", local_rank)
+    t_start = time.time()
+
+    def note(msg):
+        if os.environ.get("MCB_BENCH_VERBOSE"):
+            sys.stderr.write("[bench %7.2fs] %s\n" % (time.time() - t_start, msg))
+            sys.stderr.flush()
+
     torch.manual_seed(1234)
     model = PyTorchUNetWeighted(**unet_config("ResNet%d" % args.encoder))
     model._to_device()
@@ -236,14 +272,18 @@ def main():
     def step_dev():
         last["loss"] = model._fit_loop([Xd, Td])["sum"]
 
-    for _ in range(args.warmup):
+    note("model + data ready")
+    for i in range(args.warmup):
         step_dev()
+        torch.cuda.synchronize()
+        note("warm-up step %d done" % i)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_dev = timed(step_dev, args.steps)
     clocks = sampler.stop() if sampler else None
     loss_dev = float(last["loss"])
+    note("device arm timed: %.3f ms/step" % ms_dev)
 
     # ---- end-to-end arm: pinned host batches in, loss read back each step (one step of pipelining: the loss of
     # step i is read after step i+1 has been enqueued, so the H2D copy of the next batch overlaps compute)
@@ -258,6 +298,7 @@ def main():
     for _ in range(args.warmup):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    note("e2e arm timed: %.3f ms/step" % ms_e2e)
 
     tiles = args.batch * world
     value = tiles / (ms_dev * 1e-3)
@@ -292,6 +333,7 @@ def main():
     }
     if not args.no_breakdown:
         bd, total = breakdown(fused)
+        note("breakdown done")
         line["breakdown"] = bd
         gemm = [v for k, v in bd.items() if k.startswith("conv")]
         gemm_ms = sum(v["ms"] for v in gemm)
@@ -302,6 +344,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_arm(args, sample_batch=2, steps=2, warmup=1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        note("cpu baseline done")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

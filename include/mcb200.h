@@ -136,6 +136,20 @@ int mcb_bn_eval_params(const float* gamma, const float* beta, const float* runni
 /* y = [relu](z*scale + shift [+ residual*res_scale + res_shift | + residual]) — BN + residual add + ReLU in one pass */
 int mcb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, const float* res_scale,
                  const float* res_shift, int relu, void* y, long pixels, int c, void* stream);
+/* training-mode BN + residual + ReLU with the finalisation folded in (no separate mcb_bn_finalize launch): the affine is
+ * derived in-kernel from `stats`; mean / invstd are published for the backward pass and the running statistics updated.
+ * res_bn != NULL: the residual is a raw conv output with its own training-mode BN (ResNet downsample branch). */
+typedef struct {
+  const float* stats;  /* fp32 [2c] sum, sum of squares (from mcb_conv_fwd) */
+  const float* gamma;
+  const float* beta;
+  float* running_mean; /* may be NULL */
+  float* running_var;
+  float* mean;         /* out, fp32 [c] */
+  float* invstd;       /* out, fp32 [c] */
+} mcb_bn_train;
+int mcb_bn_train_apply(const void* z, const mcb_bn_train* bn, const void* residual, const mcb_bn_train* res_bn, int relu,
+                       void* y, long pixels, int c, float momentum, float eps, void* stream);
 /* backward: g = dy * (y_mask > 0);  dbeta += sum g;  dgamma += sum g * xhat */
 int mcb_bn_bwd_reduce(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
                       float* dbeta, float* dgamma, long pixels, int c, void* stream);
@@ -211,6 +225,21 @@ int mcb_add_dropped_objects(const uint8_t* original, const uint8_t* processed, u
  * offsets int32 [planes] (exclusive prefix of the per-plane label counts); sums/counts/scores sized total_instances */
 int mcb_instance_scores(const int* labels, const void* prob, int prob_is_f64, const int* offsets, double* sums,
                         int* counts, double* scores, int total_instances, int planes, int h, int w, void* stream);
+
+/* dense_crf (src/postprocessing.py:183-225 -> pydensecrf DenseCRF2D: unary_from_softmax, addPairwiseGaussian,
+ * addPairwiseBilateral, inference(iterations)); 2 labels, Potts compatibility, symmetric normalisation, Gaussian
+ * kernels evaluated exactly inside a 13x13 window.  PARITY UNPINNED (pydensecrf absent; see oracle/post_oracle.py).
+ * probs fp32 [n][2][h][w]; rgb uint8 [n][h][w][3]; out fp32 [n][2][h][w]; workspace fp32 [3*n*2*h*w] */
+int mcb_crf_rgb_from_normalized(const float* img_nchw, uint8_t* rgb, int n, int h, int w, void* stream);
+int mcb_dense_crf(const float* probs, const uint8_t* rgb, float* out, float* workspace, int n, int h, int w,
+                  float compat_gaussian, float sxy_gaussian, float compat_bilateral, float sxy_bilateral, float srgb,
+                  int iterations, void* stream);
+
+/* Marker-based watershed on -prob, 4-connectivity.  NOT in the reference; semantics defined by
+ * oracle/post_oracle.py::minimax_watershed (minimax flooding cost, geodesic tie-break, smallest label), PARITY UNPINNED.
+ * prob fp32|fp64, markers int32 (0 = none), mask uint8, labels int32, all [planes][h][w]; workspace int32 [3*planes*h*w] */
+int mcb_watershed(const void* prob, int prob_is_f64, const int* markers, const uint8_t* mask, int* labels,
+                  int* workspace, int planes, int h, int w, int levels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -128,3 +128,23 @@ _SIGS2 = {
 for _n, _a in _SIGS2.items():
     getattr(lib, _n).argtypes = _a
     getattr(lib, _n).restype = ci
+
+_SIGS3 = {
+    "mcb_crf_rgb_from_normalized": [vp, vp, ci, ci, ci, vp],
+    "mcb_dense_crf": [vp, vp, vp, vp, ci, ci, ci, cf, cf, cf, cf, cf, ci, vp],
+}
+for _n, _a in _SIGS3.items():
+    getattr(lib, _n).argtypes = _a
+    getattr(lib, _n).restype = ci
+
+lib.mcb_watershed.argtypes = [vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+lib.mcb_watershed.restype = ci
+
+
+class BNTrain(C.Structure):
+    _fields_ = [("stats", vp), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp), ("mean", vp),
+                ("invstd", vp)]
+
+
+lib.mcb_bn_train_apply.argtypes = [vp, C.POINTER(BNTrain), vp, C.POINTER(BNTrain), ci, vp, cl, ci, cf, cf, vp]
+lib.mcb_bn_train_apply.restype = ci

@@ -140,35 +140,131 @@ __global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const flo
 }
 
 // y = [relu]( z*scale + shift  [+ r*rscale + rshift | + r] )
-__global__ void bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const uint4* __restrict__ r,
-                                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
-                                uint4* __restrict__ y, long total8, int C8) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % C8) * 8;
-    float f[8];
-    unpack8(__ldg(z + i), f);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
-    const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), t1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+// The grid stride is a multiple of C/8, so every thread keeps ONE channel group for its whole loop and the per-channel
+// coefficients live in registers; two independent 16-byte loads per stream are in flight per iteration.
+template <int RES>  // 0: none, 1: activation residual, 2: residual with its own BN affine
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const uint4* __restrict__ r,
+                                                       const float* __restrict__ rscale, const float* __restrict__ rshift,
+                                                       int relu, uint4* __restrict__ y, long total8, int C8) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int c0 = (int)(i % C8) * 8;
+  float sc[8], sh[8], rs[8], rh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-    if (r != nullptr) {
-      float g[8];
-      unpack8(__ldg(r + i), g);
-      if (rscale != nullptr) {
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + c0 + j);
+    sh[j] = __ldg(shift + c0 + j);
+    if (RES == 2) { rs[j] = __ldg(rscale + c0 + j); rh[j] = __ldg(rshift + c0 + j); }
+  }
+  for (; i < total8; i += 2 * stride) {
+    const long i2 = i + stride;
+    const bool has2 = i2 < total8;
+    const uint4 za = __ldg(z + i);
+    uint4 zb = za, ra = za, rb = za;
+    if (has2) zb = __ldg(z + i2);
+    if (RES) { ra = __ldg(r + i); if (has2) rb = __ldg(r + i2); }
+    float f[8], g[8];
+    unpack8(za, f);
+    if (RES) unpack8(ra, g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = fmaf(g[j], __ldg(rscale + c0 + j), __ldg(rshift + c0 + j));
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += g[j];
-    }
-    if (relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (RES == 1) f[j] += g[j];
+      if (RES == 2) f[j] += fmaf(g[j], rs[j], rh[j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
     }
     y[i] = pack8(f);
+    if (has2) {
+      unpack8(zb, f);
+      if (RES) unpack8(rb, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (RES == 1) f[j] += g[j];
+        if (RES == 2) f[j] += fmaf(g[j], rs[j], rh[j]);
+        if (relu) f[j] = fmaxf(f[j], 0.f);
+      }
+      y[i2] = pack8(f);
+    }
+  }
+}
+
+// Training-mode BatchNorm with the statistics finalisation folded in: every thread derives the affine of ITS 8
+// channels from the conv epilogue's (sum, sumsq); the first C/8 threads of block 0 also publish mean / invstd for the
+// backward pass and update the running statistics (momentum, unbiased variance) — no separate finalize launch.
+struct BNTrain {
+  const float* stats;   // [2C] sum, sumsq
+  const float* gamma;
+  const float* beta;
+  float* running_mean;  // may be null
+  float* running_var;
+  float* mean;          // saved for backward
+  float* invstd;
+};
+__device__ __forceinline__ void bn_train_coef(const BNTrain& b, int C, int c0, float count, float eps, float momentum,
+                                              bool writer, float (&sc)[8], float (&sh)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float mean = __ldg(b.stats + c) / count;
+    const float var = fmaxf(__ldg(b.stats + C + c) / count - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    sc[j] = __ldg(b.gamma + c) * invstd;
+    sh[j] = __ldg(b.beta + c) - mean * sc[j];
+    if (writer) {
+      b.mean[c] = mean;
+      b.invstd[c] = invstd;
+      if (b.running_mean != nullptr) {
+        const float unbiased = var * (count / fmaxf(count - 1.f, 1.f));
+        b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mean;
+        b.running_var[c] = (1.f - momentum) * b.running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+}
+template <int RES>
+__global__ void __launch_bounds__(256) bn_train_apply_kernel(const uint4* __restrict__ z, BNTrain bn,
+                                                             const uint4* __restrict__ r, BNTrain rbn, int relu,
+                                                             uint4* __restrict__ y, long total8, int C8, float count,
+                                                             float eps, float momentum) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int c0 = (int)(i % C8) * 8;
+  const bool writer = (i < C8);
+  float sc[8], sh[8], rs[8], rh[8];
+  bn_train_coef(bn, C8 * 8, c0, count, eps, momentum, writer, sc, sh);
+  if (RES == 2) bn_train_coef(rbn, C8 * 8, c0, count, eps, momentum, writer, rs, rh);
+  for (; i < total8; i += 2 * stride) {
+    const long i2 = i + stride;
+    const bool has2 = i2 < total8;
+    const uint4 za = __ldg(z + i);
+    uint4 zb = za, ra = za, rb = za;
+    if (has2) zb = __ldg(z + i2);
+    if (RES) { ra = __ldg(r + i); if (has2) rb = __ldg(r + i2); }
+    float f[8], g[8];
+    unpack8(za, f);
+    if (RES) unpack8(ra, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (RES == 1) f[j] += g[j];
+      if (RES == 2) f[j] += fmaf(g[j], rs[j], rh[j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    y[i] = pack8(f);
+    if (has2) {
+      unpack8(zb, f);
+      if (RES) unpack8(rb, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (RES == 1) f[j] += g[j];
+        if (RES == 2) f[j] += fmaf(g[j], rs[j], rh[j]);
+        if (relu) f[j] = fmaxf(f[j], 0.f);
+      }
+      y[i2] = pack8(f);
+    }
   }
 }
 
@@ -196,25 +292,43 @@ __global__ void channel_reduce_kernel(const uint4* __restrict__ a, const uint4* 
     }
   }
   if (lane_p < lanes) {
-    for (long p = (long)blockIdx.x * lanes + lane_p; p < pixels; p += (long)gridDim.x * lanes) {
-      const long i = p * C8 + cg;
-      float f[8];
-      unpack8(__ldg(a + i), f);
-      if (MODE == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s0[j] += f[j];
-      } else {
-        float m[8], zz[8];
-        unpack8(__ldg(z + i), zz);
+    const long pstride = (long)gridDim.x * lanes;
+    for (long p = (long)blockIdx.x * lanes + lane_p; p < pixels; p += 2 * pstride) {
+      const long ia = p * C8 + cg;
+      const long ib = (p + pstride) * C8 + cg;
+      const bool hb = (p + pstride) < pixels;
+      const uint4 va = __ldg(a + ia);
+      uint4 vb = va, za = va, zb = va, ma = va, mb = va;
+      if (hb) vb = __ldg(a + ib);
+      if (MODE == 1) {
+        za = __ldg(z + ia);
+        if (hb) zb = __ldg(z + ib);
         if (ymask != nullptr) {
-          unpack8(__ldg(ymask + i), m);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = (m[j] > 0.f) ? f[j] : 0.f;
+          ma = __ldg(ymask + ia);
+          if (hb) mb = __ldg(ymask + ib);
         }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s0[j] += f[j];
-          s1[j] += f[j] * ((zz[j] - mu[j]) * is[j]);
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !hb) break;
+        float f[8];
+        unpack8(u ? vb : va, f);
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s0[j] += f[j];
+        } else {
+          float m[8], zz[8];
+          unpack8(u ? zb : za, zz);
+          if (ymask != nullptr) {
+            unpack8(u ? mb : ma, m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (m[j] > 0.f) ? f[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s0[j] += f[j];
+            s1[j] += f[j] * ((zz[j] - mu[j]) * is[j]);
+          }
         }
       }
     }
@@ -241,39 +355,67 @@ __global__ void channel_reduce_kernel(const uint4* __restrict__ a, const uint4* 
 }
 
 // dz = gamma*invstd * (g - dbeta/M - xhat * dgamma/M),  g = dy * (y > 0); optionally also emits g (the gradient that
-// flows to the residual branch): g_out = g (store) or g_out += g (accumulate)
-__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ymask,
-                                    const uint4* __restrict__ z, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ dbeta, const float* __restrict__ dgamma, float inv_count,
-                                    uint4* __restrict__ dz, uint4* __restrict__ g_out, int g_accumulate, long total8,
-                                    int C8) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % C8) * 8;
-    float g[8], zz[8], o[8];
-    unpack8(__ldg(dy + i), g);
-    unpack8(__ldg(z + i), zz);
-    if (ymask != nullptr) {
-      float m[8];
-      unpack8(__ldg(ymask + i), m);
+// flows to the residual branch): g_out = g (store) or g_out += g (accumulate).  Per-channel coefficients in registers
+// (fixed channel group per thread), two independent loads per stream in flight.
+template <bool MASK, int GOUT>  // GOUT 0: none, 1: store, 2: accumulate
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ymask,
+                                                           const uint4* __restrict__ z, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                           float inv_count, uint4* __restrict__ dz, uint4* __restrict__ g_out,
+                                                           long total8, int C8) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int c0 = (int)(i % C8) * 8;
+  float mu[8], is[8], a[8], k1[8], k2[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f) ? g[j] : 0.f;
-    }
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = __ldg(mean + c0 + j);
+    is[j] = __ldg(invstd + c0 + j);
+    a[j] = __ldg(gamma + c0 + j) * is[j];
+    k1[j] = __ldg(dbeta + c0 + j) * inv_count;
+    k2[j] = __ldg(dgamma + c0 + j) * inv_count;
+  }
+  for (; i < total8; i += 2 * stride) {
+    const long idx[2] = {i, i + stride};
+    const bool has[2] = {true, idx[1] < total8};
+    uint4 vdy[2], vz[2], vm[2], vg[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float is = __ldg(invstd + c0 + j);
-      const float xh = (zz[j] - __ldg(mean + c0 + j)) * is;
-      o[j] = __ldg(gamma + c0 + j) * is * (g[j] - __ldg(dbeta + c0 + j) * inv_count - xh * __ldg(dgamma + c0 + j) * inv_count);
-    }
-    dz[i] = pack8(o);
-    if (g_out != nullptr) {
-      if (g_accumulate) {
-        float e[8];
-        unpack8(g_out[i], e);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += e[j];
+    for (int u = 0; u < 2; ++u) {
+      if (has[u]) {
+        vdy[u] = __ldg(dy + idx[u]);
+        vz[u] = __ldg(z + idx[u]);
+        if (MASK) vm[u] = __ldg(ymask + idx[u]);
+        if (GOUT == 2) vg[u] = g_out[idx[u]];
       }
-      g_out[i] = pack8(g);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!has[u]) continue;
+      float g[8], zz[8], o[8];
+      unpack8(vdy[u], g);
+      unpack8(vz[u], zz);
+      if (MASK) {
+        float m[8];
+        unpack8(vm[u], m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f) ? g[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (zz[j] - mu[j]) * is[j];
+        o[j] = a[j] * (g[j] - k1[j] - xh * k2[j]);
+      }
+      dz[idx[u]] = pack8(o);
+      if (GOUT) {
+        if (GOUT == 2) {
+          float e[8];
+          unpack8(vg[u], e);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += e[j];
+        }
+        g_out[idx[u]] = pack8(g);
+      }
     }
   }
 }
@@ -509,9 +651,41 @@ extern "C" int mcb_bn_apply(const void* z, const float* scale, const float* shif
                             void* stream) {
   MCB_REQUIRE(z && scale && shift && y, "bn_apply: null pointer");
   MCB_REQUIRE(c % 8 == 0, "bn_apply: channels %d not a multiple of 8", c);
+  MCB_REQUIRE(256 % (c / 8) == 0, "bn_apply: channels %d (c/8 must divide 256)", c);
   const long total8 = pixels * (c / 8);
-  bn_apply_kernel<<<grid_for(total8, 256), 256, 0, ST>>>((const uint4*)z, scale, shift, (const uint4*)residual,
-                                                         res_scale, res_shift, relu, (uint4*)y, total8, c / 8);
+  const int grid = grid_for((total8 + 1) / 2, 256);
+  if (residual == nullptr)
+    bn_apply_kernel<0><<<grid, 256, 0, ST>>>((const uint4*)z, scale, shift, nullptr, nullptr, nullptr, relu, (uint4*)y,
+                                             total8, c / 8);
+  else if (res_scale == nullptr)
+    bn_apply_kernel<1><<<grid, 256, 0, ST>>>((const uint4*)z, scale, shift, (const uint4*)residual, nullptr, nullptr,
+                                             relu, (uint4*)y, total8, c / 8);
+  else
+    bn_apply_kernel<2><<<grid, 256, 0, ST>>>((const uint4*)z, scale, shift, (const uint4*)residual, res_scale,
+                                             res_shift, relu, (uint4*)y, total8, c / 8);
+  MCB_LAUNCH_CHECK();
+  return MCB_OK;
+}
+
+extern "C" int mcb_bn_train_apply(const void* z, const mcb_bn_train* bn, const void* residual,
+                                  const mcb_bn_train* res_bn, int relu, void* y, long pixels, int c, float momentum,
+                                  float eps, void* stream) {
+  MCB_REQUIRE(z && bn && y && bn->stats && bn->gamma && bn->beta && bn->mean && bn->invstd, "bn_train_apply: null pointer");
+  MCB_REQUIRE(c % 8 == 0 && 256 % (c / 8) == 0, "bn_train_apply: channels %d (c/8 must divide 256)", c);
+  MCB_REQUIRE(!(res_bn && !residual), "bn_train_apply: res_bn without residual");
+  const long total8 = pixels * (c / 8);
+  const int grid = grid_for((total8 + 1) / 2, 256);
+  BNTrain b{bn->stats, bn->gamma, bn->beta, bn->running_mean, bn->running_var, bn->mean, bn->invstd};
+  BNTrain rb{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (res_bn) rb = BNTrain{res_bn->stats, res_bn->gamma, res_bn->beta, res_bn->running_mean, res_bn->running_var,
+                           res_bn->mean, res_bn->invstd};
+  const float count = (float)pixels;
+  if (residual == nullptr)
+    bn_train_apply_kernel<0><<<grid, 256, 0, ST>>>((const uint4*)z, b, nullptr, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
+  else if (res_bn == nullptr)
+    bn_train_apply_kernel<1><<<grid, 256, 0, ST>>>((const uint4*)z, b, (const uint4*)residual, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
+  else
+    bn_train_apply_kernel<2><<<grid, 256, 0, ST>>>((const uint4*)z, b, (const uint4*)residual, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }
@@ -551,10 +725,21 @@ extern "C" int mcb_bn_bwd_apply(const void* dy, const void* y_mask, const void* 
                                 void* dz, void* g_out, int g_accumulate, long pixels, int c, void* stream) {
   MCB_REQUIRE(dy && z && mean && invstd && gamma && dbeta && dgamma && dz, "bn_bwd_apply: null pointer");
   MCB_REQUIRE(c % 8 == 0, "bn_bwd_apply: channels %d", c);
+  MCB_REQUIRE(256 % (c / 8) == 0, "bn_bwd_apply: channels %d (c/8 must divide 256)", c);
   const long total8 = pixels * (c / 8);
-  bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, ST>>>(
-      (const uint4*)dy, (const uint4*)y_mask, (const uint4*)z, mean, invstd, gamma, dbeta, dgamma,
-      1.0f / (float)pixels, (uint4*)dz, (uint4*)g_out, g_accumulate, total8, c / 8);
+  const int grid = grid_for((total8 + 1) / 2, 256);
+  const float ic = 1.0f / (float)pixels;
+#define MCB_BWD(MASK, GOUT)                                                                                         \
+  bn_bwd_apply_kernel<MASK, GOUT><<<grid, 256, 0, ST>>>((const uint4*)dy, (const uint4*)y_mask, (const uint4*)z, mean, \
+                                                        invstd, gamma, dbeta, dgamma, ic, (uint4*)dz, (uint4*)g_out,  \
+                                                        total8, c / 8)
+  const int gout = g_out == nullptr ? 0 : (g_accumulate ? 2 : 1);
+  if (y_mask != nullptr) {
+    if (gout == 0) MCB_BWD(true, 0); else if (gout == 1) MCB_BWD(true, 1); else MCB_BWD(true, 2);
+  } else {
+    if (gout == 0) MCB_BWD(false, 0); else if (gout == 1) MCB_BWD(false, 1); else MCB_BWD(false, 2);
+  }
+#undef MCB_BWD
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

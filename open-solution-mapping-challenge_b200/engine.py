@@ -18,10 +18,10 @@ F32 = torch.float32
 
 class _Op:
     """one launch (or a tiny group) with its algorithmic cost, for the per-kernel breakdown in bench.py"""
-    __slots__ = ("kind", "fn", "flops", "bytes")
+    __slots__ = ("kind", "fn", "flops", "bytes", "desc")
 
-    def __init__(self, kind, fn, flops=0.0, nbytes=0.0):
-        self.kind, self.fn, self.flops, self.bytes = kind, fn, float(flops), float(nbytes)
+    def __init__(self, kind, fn, flops=0.0, nbytes=0.0, desc=""):
+        self.kind, self.fn, self.flops, self.bytes, self.desc = kind, fn, float(flops), float(nbytes), desc
 
     def __call__(self):
         return self.fn()
@@ -34,13 +34,13 @@ def _nb(*tensors):
 class _OpList(list):
     """list of _Op; .add(kind, fn, flops, bytes)"""
 
-    def add(self, kind, fn, flops=0.0, nbytes=0.0):
-        self.append(_Op(kind, fn, flops, nbytes))
+    def add(self, kind, fn, flops=0.0, nbytes=0.0, desc=""):
+        self.append(_Op(kind, fn, flops, nbytes, desc))
 
 
 class _BN:
     """per-BatchNorm device state"""
-    __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta")
+    __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta", "tr")
 
 
 class Plan:
@@ -101,6 +101,8 @@ class Plan:
         b.scale, b.shift, b.mean, b.invstd = buf[:c], buf[c:2 * c], buf[2 * c:3 * c], buf[3 * c:4 * c]
         b.gamma, b.beta = net._vec(mod.weight, net._p32), net._vec(mod.bias, net._p32)
         b.dgamma, b.dbeta = net._vec(mod.weight, net._g32), net._vec(mod.bias, net._g32)
+        b.tr = ops.make_bn_train(b.stats, b.gamma, b.beta, mod.running_mean, mod.running_var, b.mean, b.invstd) \
+            if self.training else None
         self._bns.append(b)
         return b
 
@@ -117,12 +119,9 @@ class Plan:
         w16 = net._packed(conv.weight, net._w16)
         F = self.fwd_ops
         cflops = 2.0 * z.numel() * cin * k * k
+        desc = "%d->%d k%d s%d @%dx%dx%d" % (cin, cout, k, s, n, h, w)
         if self.training:
-            F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z), cflops, _nb(x, w16, z))
-            cnt = z.numel() // cout
-            F.add("bn_finalize", lambda: ops.bn_finalize(bn.stats, cnt, bn.gamma, bn.beta, bnmod.running_mean,
-                                                        bnmod.running_var, bn.scale, bn.shift, bn.mean, bn.invstd,
-                                                        BN_MOMENTUM, BN_EPS))
+            F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z), cflops, _nb(x, w16, z), desc)
         else:
             F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, out=z), cflops, _nb(x, w16, z))
             F.add("bn_finalize", lambda: ops.bn_eval_params(bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var,
@@ -130,13 +129,21 @@ class Plan:
         if relu is None:
             return None, z, bn
         y = out if out is not None else self.act(*z.shape)
-        if res_bn is not None:
-            rb = res_bn
-            F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, rb.scale, rb.shift),
-                  0, _nb(z, y, residual))
+        self.bn_apply_op(z, bn, y, relu, residual, res_bn)
+        return y, z, bn
+
+    def bn_apply_op(self, z, bn, y, relu, residual=None, res_bn=None):
+        """BN (+residual [+ its BN]) + ReLU in one pass; training mode folds the statistics finalisation in"""
+        F = self.fwd_ops
+        if self.training:
+            rtr = res_bn.tr if res_bn is not None else None
+            F.add("bn_apply", lambda: ops.bn_train_apply(z, bn.tr, y, relu, residual, rtr, BN_MOMENTUM, BN_EPS), 0,
+                  _nb(z, y, residual))
+        elif res_bn is not None:
+            F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, res_bn.scale,
+                                                   res_bn.shift), 0, _nb(z, y, residual))
         else:
             F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual), 0, _nb(z, y, residual))
-        return y, z, bn
 
     def conv_unit_backward(self, B, dy, ymask, z, bn, conv, x, g_out=None, g_out_acc=False):
         """backward of y = relu(bn(conv(x)) [+ r]) given dy = dL/dy: BN reductions + dz, wgrad, dgrad into grad(x).
@@ -150,8 +157,9 @@ class Plan:
               _nb(dy, ymask, z))
         B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma,
                                                       dz, g_out, g_out_acc), 0, _nb(dy, ymask, z, dz, g_out))
+        desc = "%d->%d k%d s%d @%dx%dx%d" % (x.shape[3], dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2])
         B.add("conv_wgrad", lambda: ops.conv_wgrad(dz, x, gw, k, s), 2.0 * dz.numel() * x.shape[3] * k * k,
-              _nb(dz, x, gw))
+              _nb(dz, x, gw), desc)
         return dz
 
     def dgrad_into(self, B, dz, conv, x, relu_mask=None, ci_off=0):
@@ -167,7 +175,9 @@ class Plan:
             raise RuntimeError("plan error: masked dgrad cannot accumulate")
         B.add("conv_dgrad", lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
                                                    accumulate=acc, out=gx), 2.0 * dz.numel() * cin * k * k,
-              _nb(dz, gx, relu_mask) + (_nb(gx) if acc else 0) + 2.0 * k * k * dz.shape[3] * cin)
+              _nb(dz, gx, relu_mask) + (_nb(gx) if acc else 0) + 2.0 * k * k * dz.shape[3] * cin,
+              "%d<-%d k%d s%d @%dx%dx%d%s" % (cin, dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2],
+                                              " acc" if acc else ""))
 
     # ------------------------------------------------------------------------------------------ network
     def _build(self):
@@ -188,16 +198,12 @@ class Plan:
         bn0 = self.bn_state(enc.bn1)
         if train:
             F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, stats=bn0.stats, out=z0), sflops, _nb(col, z0))
-            cnt0 = z0.numel() // 64
-            F.add("bn_finalize", lambda: ops.bn_finalize(bn0.stats, cnt0, bn0.gamma, bn0.beta, enc.bn1.running_mean,
-                                                        enc.bn1.running_var, bn0.scale, bn0.shift, bn0.mean,
-                                                        bn0.invstd, BN_MOMENTUM, BN_EPS))
         else:
             F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, out=z0), sflops, _nb(col, z0))
             F.add("bn_finalize", lambda: ops.bn_eval_params(bn0.gamma, bn0.beta, enc.bn1.running_mean,
                                                            enc.bn1.running_var, bn0.scale, bn0.shift, BN_EPS))
         a0 = self.act(*z0.shape)
-        F.add("bn_apply", lambda: ops.bn_apply(z0, bn0.scale, bn0.shift, a0, True), 0, _nb(z0, a0))
+        self.bn_apply_op(z0, bn0, a0, True)
         c1 = self.act(n, h // 4, w // 4, 64)
         F.add("maxpool", lambda: ops.maxpool2_fwd(a0, c1), 0, _nb(a0, c1))
         if train:
@@ -287,10 +293,9 @@ class Plan:
         if blk.downsample is not None:
             dconv, dbnm = blk.downsample[0], blk.downsample[1]
             _, zd, bnd = self.conv_bn(x, dconv, dbnm, None)
-            F.add("bn_apply", lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, zd, bnd.scale, bnd.shift), 0,
-                  _nb(z_l, out, zd))
+            self.bn_apply_op(z_l, bnl, out, True, zd, bnd)
         else:
-            F.add("bn_apply", lambda: ops.bn_apply(z_l, bnl.scale, bnl.shift, out, True, x), 0, _nb(z_l, out, x))
+            self.bn_apply_op(z_l, bnl, out, True, x)
         if train:
             last_in = cur
 
@@ -334,8 +339,9 @@ class Plan:
         fc = 2.0 * mid.numel() * ctot * 9
         ft = 2.0 * mid.numel() * cout * 16
         F.add("conv_fwd", lambda: ops.conv_fwd(x1, w16, 3, 1, bias=b1, relu=True, x2=skip, out=mid), fc,
-              _nb(x1, skip, w16, mid))
-        F.add("convt_fwd", lambda: ops.convt_fwd(mid, wt16, bias=b2, relu=True, out=out), ft, _nb(mid, wt16, out))
+              _nb(x1, skip, w16, mid), "dec %d->%d k3 @%dx%dx%d" % (ctot, cmid, n, h, w))
+        F.add("convt_fwd", lambda: ops.convt_fwd(mid, wt16, bias=b2, relu=True, out=out), ft, _nb(mid, wt16, out),
+              "%d->%d @%dx%dx%d" % (cmid, cout, n, h, w))
         if self.training:
             def build_dec(B):
                 g_out = self.gbuf(out)   # already masked by out's ReLU (the consumer's dgrad epilogue did it)
@@ -345,15 +351,17 @@ class Plan:
                 gw = net._packed(conv.weight, net._g32)
                 gb1 = net._vec(conv.bias, net._g32)
                 B.add("channel_sum", lambda: ops.channel_sum(g_out, gb2), 0, _nb(g_out))
-                B.add("convt_wgrad", lambda: ops.convt_wgrad(g_out, mid, gwt), ft, _nb(g_out, mid, gwt))
+                dd = "%d->%d @%dx%dx%d" % (cmid, cout, n, h, w)
+                B.add("convt_wgrad", lambda: ops.convt_wgrad(g_out, mid, gwt), ft, _nb(g_out, mid, gwt), dd)
                 B.add("convt_dgrad", lambda: ops.convt_dgrad(g_out, wt16, relu_mask=mid, out=g_mid), ft,
-                      _nb(g_out, wt16, mid, g_mid))
+                      _nb(g_out, wt16, mid, g_mid), dd)
                 B.add("channel_sum", lambda: ops.channel_sum(g_mid, gb1), 0, _nb(g_mid))
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(g_mid, x1, gw, 3, 1, ci_off=0),
-                      2.0 * mid.numel() * c1 * 9, _nb(g_mid, x1))
+                      2.0 * mid.numel() * c1 * 9, _nb(g_mid, x1), "dec %d->%d k3 @%dx%dx%d" % (c1, cmid, n, h, w))
                 if skip is not None:
                     B.add("conv_wgrad", lambda: ops.conv_wgrad(g_mid, skip, gw, 3, 1, ci_off=c1),
-                          2.0 * mid.numel() * skip.shape[3] * 9, _nb(g_mid, skip))
+                          2.0 * mid.numel() * skip.shape[3] * 9, _nb(g_mid, skip),
+                          "dec-skip %d->%d k3 @%dx%dx%d" % (skip.shape[3], cmid, n, h, w))
                 # x1 is a decoder ReLU output (mask in the epilogue) unless it is the centre's max-pool output
                 self.dgrad_into(B, g_mid, conv, x1, relu_mask=None if pool_input else x1, ci_off=0)
                 if skip is not None:

@@ -198,6 +198,23 @@ def bn_apply(z, scale, shift, out, relu=True, residual=None, res_scale=None, res
     return out
 
 
+def make_bn_train(stats, gamma, beta, rm, rv, mean, invstd):
+    b = L.BNTrain()
+    b.stats, b.gamma, b.beta = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+    b.running_mean, b.running_var = L.dp(rm), L.dp(rv)
+    b.mean, b.invstd = mean.data_ptr(), invstd.data_ptr()
+    return b
+
+
+def bn_train_apply(z, bn, out, relu=True, residual=None, res_bn=None, momentum=0.1, eps=1e-5):
+    """bn / res_bn: L.BNTrain structs (make_bn_train); statistics finalisation folded into the apply pass"""
+    c = z.shape[-1]
+    L.fcall("mcb_bn_train_apply", _chk(z).data_ptr(), C.byref(bn), L.dp(residual),
+            C.byref(res_bn) if res_bn is not None else None, int(relu), _chk(out).data_ptr(), z.numel() // c, c,
+            momentum, eps)
+    return out
+
+
 def bn_bwd_reduce(dy, y_mask, z, mean, invstd, dbeta, dgamma):
     c = z.shape[-1]
     L.fcall("mcb_bn_bwd_reduce", _chk(dy).data_ptr(), L.dp(y_mask), _chk(z).data_ptr(), mean.data_ptr(),

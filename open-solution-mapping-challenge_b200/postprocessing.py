@@ -205,6 +205,56 @@ def build_score(image, probabilities):
     return image, total
 
 
+def dense_crf_batch(imgs, probs, compat_gaussian=3, sxy_gaussian=1, compat_bilateral=10, sxy_bilateral=1, srgb=50,
+                    iterations=5):
+    """imgs (N,3,H,W) float32 ImageNet-normalised, probs (N,2,H,W) float32, both cuda -> (N,2,H,W) float32"""
+    assert imgs.is_cuda and probs.is_cuda and imgs.dtype == torch.float32 and probs.dtype == torch.float32
+    imgs, probs = imgs.contiguous(), probs.contiguous()
+    n, c, h, w = probs.shape
+    if c != 2:
+        raise NotImplementedError("dense_crf: 2 labels (the reference builds DenseCRF2D(width, height, 2))")
+    rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, device=probs.device)
+    L.fcall("mcb_crf_rgb_from_normalized", imgs.data_ptr(), rgb.data_ptr(), n, h, w)
+    out = torch.empty_like(probs)
+    ws = torch.empty(3 * probs.numel(), dtype=torch.float32, device=probs.device)
+    L.fcall("mcb_dense_crf", probs.data_ptr(), rgb.data_ptr(), out.data_ptr(), ws.data_ptr(), n, h, w,
+            float(compat_gaussian), float(sxy_gaussian), float(compat_bilateral), float(sxy_bilateral), float(srgb),
+            int(iterations))
+    return out
+
+
+def dense_crf(img, output_probs, compat_gaussian=3, sxy_gaussian=1, compat_bilateral=10, sxy_bilateral=1, srgb=50,
+              iterations=5):
+    """src/postprocessing.py:183-225 (parity unpinned: pydensecrf is absent; semantics in oracle/post_oracle.py)"""
+    x = _to_dev(np.asarray(img), torch.float32)[None]
+    p = _to_dev(np.asarray(output_probs), torch.float32)[None]
+    return dense_crf_batch(x, p, compat_gaussian, sxy_gaussian, compat_bilateral, sxy_bilateral, srgb,
+                           iterations)[0].cpu().numpy()
+
+
+def watershed_batch(prob, markers, mask, levels=256):
+    """prob (P,H,W) float32|float64, markers (P,H,W) int32, mask (P,H,W) uint8|bool, cuda -> int32 labels.
+    Not a reference function; semantics = oracle/post_oracle.py::minimax_watershed (parity unpinned)."""
+    assert prob.is_cuda and prob.dtype in (torch.float32, torch.float64)
+    prob, markers = prob.contiguous(), markers.contiguous().to(torch.int32)
+    mask = mask.contiguous()
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    p, h, w = prob.shape
+    out = torch.empty((p, h, w), dtype=torch.int32, device=prob.device)
+    ws = torch.empty(3 * p * h * w, dtype=torch.int32, device=prob.device)
+    L.fcall("mcb_watershed", prob.data_ptr(), int(prob.dtype == torch.float64), markers.data_ptr(), mask.data_ptr(),
+            out.data_ptr(), ws.data_ptr(), p, h, w, int(levels))
+    return out
+
+
+def watershed_split(prob, hi=0.8, lo=0.5, levels=256):
+    """instance split of touching buildings: markers = components of prob > hi, flooded over prob > lo"""
+    hi_mask = (prob > hi).to(torch.uint8).contiguous()
+    markers = label_batch(hi_mask)
+    return watershed_batch(prob, markers, (prob > lo).to(torch.uint8), levels)
+
+
 def crop_image_center_per_class(image, h_crop, w_crop):
     """src/postprocessing.py:239-258 — pure indexing"""
     out = []

@@ -113,6 +113,24 @@ def test_batchnorm_train_forward_backward(mcb, cuda, c, n, h, w, residual):
     else:
         ops.bn_apply(zd, scale, shift, yd, True)
     close(nchw(yd), out.detach(), atol=1e-2)
+    # fused finalize + apply (what the training plan launches) == the two-step path
+    rm2, rv2 = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+    mean2, inv2 = torch.empty(c, device=cuda), torch.empty(c, device=cuda)
+    tr = ops.make_bn_train(stats, gm, bt, rm2, rv2, mean2, inv2)
+    y2 = torch.empty_like(zd)
+    if residual == "bn":
+        rg, rbt = rgamma.to(cuda), rbeta.to(cuda)
+        rmean2, rinv2 = torch.empty(c, device=cuda), torch.empty(c, device=cuda)
+        rtr = ops.make_bn_train(rstats, rg, rbt, None, None, rmean2, rinv2)
+        ops.bn_train_apply(zd, tr, y2, True, rd, rtr)
+        assert torch.allclose(rmean2, rmean) and torch.allclose(rinv2, rinv)
+    elif residual == "act":
+        ops.bn_train_apply(zd, tr, y2, True, rd)
+    else:
+        ops.bn_train_apply(zd, tr, y2, True)
+    assert torch.equal(y2, yd)
+    assert torch.allclose(mean2, mean) and torch.allclose(inv2, invstd)
+    assert torch.allclose(rm2, rmd) and torch.allclose(rv2, rvd)
     # backward (mask from the stored bf16 output, like the plan does)
     dyd = nhwc(dy).to(cuda, BF)
     dbeta, dgamma = torch.zeros(c, device=cuda), torch.zeros(c, device=cuda)
