@@ -48,7 +48,7 @@ static int launch_conv_inst(const ConvGemmParams& p, dim3 grid, size_t smem, cud
                                         227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, BK, B_MN><<<grid, kGemmThreads, smem, st>>>(p);
+  conv_gemm_kernel<BN, BK, B_MN><<<grid, kConvThreads, smem, st>>>(p);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }
@@ -68,20 +68,16 @@ static int launch_conv(int BN, int BK, bool b_mn, ConvGemmParams& p, int m_tiles
                        cudaStream_t st) {
   const int a_bytes = 128 * BK * 2, b_bytes = BN * BK * 2;
   const int stage = a_bytes + b_bytes;
-  int max_kb = 0;
-  for (int ph = 0; ph < phases; ++ph) {
-    int kb = 0;
-    for (int t = p.tap_start[ph]; t < p.tap_start[ph] + p.tap_count[ph]; ++t) kb += p.taps[t].nchunks;
-    max_kb = std::max(max_kb, kb);
-  }
-  const int budget = env_int("MCB_SMEM_BUDGET_KB", 110) * 1024;
-  int stages = std::max(2, std::min(std::min(max_kb, 8), budget / stage));
-  // the epilogue stages the bf16 output tile in the pipeline buffers
   const int out_bytes = 128 * BN * 2;
-  while (stages * stage < out_bytes) ++stages;
+  const int stat_bytes = 16 * 1024;  // (2048 / BN row groups) x BN columns x {sum, sumsq} floats == 16 KB for every BN
+  const int fixed = out_bytes + stat_bytes + 1024 /*align*/ + 512 /*barriers*/;
+  const int budget = std::min(env_int("MCB_SMEM_BUDGET_KB", 227) * 1024, 232448);
+  int stages = std::max(2, std::min(env_int("MCB_MAX_STAGES", 6), (budget - fixed) / stage));
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage + 1024 + 512;
-  dim3 grid(m_tiles, n_tiles, phases);
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.phases = phases;
+  const size_t smem = (size_t)stages * stage + fixed;
+  const long total = (long)m_tiles * n_tiles * phases;
+  dim3 grid((unsigned)std::min<long>(total, num_sms()), 1, 1);
   if (BK == 64) return b_mn ? launch_conv_bn<64, true>(BN, p, grid, smem, st) : launch_conv_bn<64, false>(BN, p, grid, smem, st);
   return b_mn ? launch_conv_bn<32, true>(BN, p, grid, smem, st) : launch_conv_bn<32, false>(BN, p, grid, smem, st);
 }
@@ -93,7 +89,9 @@ static int pick_bn(int n_total, long m_tiles, int phases) {
   }
   // keep the machine filled when the pixel dimension is small
   const long sms = num_sms();
-  while (bn > 64 && m_tiles * phases * (n_total / bn) < sms) bn /= 2;
+  // (fat tiles beat many thin ones: go below 128 only when even 128-wide tiles leave most SMs idle)
+  if (bn > 128 && m_tiles * phases * (n_total / bn) < sms) bn = 128;
+  if (bn > 64 && n_total % 64 == 0 && m_tiles * phases * (n_total / bn) < sms / 3) bn = 64;
   int forced = env_int("MCB_FORCE_BN", 0);
   if (forced && n_total % forced == 0) bn = forced;
   return bn;
@@ -405,11 +403,17 @@ static int launch_wgrad(WgradParams& p, int cin_src, cudaStream_t st) {
   const int m_tiles = (p.cout + 127) / 128;
   const int n_tiles = cin_src / BN;
   // split-K over the pixel tiles so the grid covers the machine a few times
+  // Every split adds a full fp32 output tile with red.add (atomic traffic = splits x |dW|), while the operand
+  // streams are L2/HBM-bound and want every SM busy.  So: exactly ONE resident wave of CTAs (never a ragged second
+  // wave) and at least `min_kb` K blocks per CTA (sweep: tools/sweep_gemm.py, gpurun_out/sweep1.log).
   const long base = (long)m_tiles * n_tiles * p.ntaps;
-  const long target = 3L * num_sms();
-  int splits = (int)std::max(1L, std::min((long)p.tiles_total, (target + base - 1) / base));
-  // keep at least 4 K blocks per split when there is enough work
-  splits = std::max(1, std::min(splits, std::max(1, p.tiles_total / 4)));
+  const int b_cw0 = BN >= 64 ? 64 : 32;
+  const int stage0 = 2 * 64 * 128 + (BN / b_cw0) * 64 * b_cw0 * 2;
+  const int ctas_per_sm = std::max(1, std::min(2, (227 * 1024) / (2 * stage0 + 2048)));
+  const long cap = (long)num_sms() * ctas_per_sm * env_int("MCB_WGRAD_WAVES_X10", 10) / 10;
+  int splits = (int)std::max(1L, std::min((long)p.tiles_total, cap / std::max(1L, base)));
+  const int min_kb = env_int("MCB_WGRAD_MIN_KB", 6);
+  splits = std::max(1, std::min(splits, std::max(1, p.tiles_total / min_kb)));
   int forced = env_int("MCB_WGRAD_SPLITS", 0);
   if (forced > 0) splits = std::min(forced, p.tiles_total);
   p.splits = splits;

@@ -39,6 +39,7 @@ struct ConvGemmParams {
   int Wv, Hv, Nimg;  // extents of the output view
   int bw, bh, bn, rows;
   int tiles_x, tiles_y;
+  int m_tiles, n_tiles, phases;  // persistent tile space: phases x m_tiles x n_tiles
   int stages;
   int n_off;  // first N (weight row / column) coordinate of this launch (concat source slice for dgrad)
   // epilogue
@@ -78,8 +79,13 @@ __device__ __forceinline__ uint8_t* align_up_1024(uint8_t* p) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised: one CTA per SM walks tiles t = blockIdx.x, += gridDim.x (n fastest, so CTAs that run
+// together share the A pixel tile in L2).  The TMA ring (full/empty mbarriers) runs continuously across tiles; two
+// TMEM accumulators (2 x BN columns) let the 8 epilogue warps drain tile i while the MMA warp is already on tile i+1.
+constexpr int kConvThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+
 template <int BN, int BK, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(BK == 64 || BK == 32, "BK");
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
   constexpr int A_ROW_BYTES = BK * 2;              // 128 (SW128) or 64 (SW64)
@@ -94,48 +100,50 @@ __global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const __grid_co
   constexpr int BMN_SUBS = BN / BMN_CW;
   constexpr uint32_t BMN_LAYOUT = (BMN_CW == 64) ? tc::LAYOUT_SW128 : tc::LAYOUT_SW64;
   constexpr uint32_t IDESC = tc::make_idesc_bf16(128, BN, 0, B_MN ? 1 : 0);
-  // output staging: chunks of OUT_CW channels
+  // output staging: chunks of OUT_CW channels (one TMA store each)
   constexpr int OUT_CW = (BN >= 64) ? 64 : 32;
   constexpr int OUT_ROW_BYTES = OUT_CW * 2;
   constexpr int OUT_CHUNK_BYTES = 128 * OUT_ROW_BYTES;
   constexpr int OUT_CHUNKS = BN / OUT_CW;
+  constexpr int OUT_BYTES = OUT_CHUNKS * OUT_CHUNK_BYTES;
+  // statistics scratch: RG row groups x BN columns x {sum, sumsq}
+  constexpr int CG = BN / 8;            // column groups of 8 channels
+  constexpr int RG = 256 / CG;          // row groups (256 epilogue threads)
+  constexpr int ROWS_PER_RG = 128 / RG;
+  constexpr int STAT_BYTES = RG * BN * 2 * 4;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_up_1024(smem_raw);
   const int stages = p.stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint8_t* out_stage = smem + (size_t)stages * STAGE_BYTES;            // 1024-aligned (STAGE_BYTES is)
+  float* stat_scratch = reinterpret_cast<float*>(out_stage + OUT_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + OUT_BYTES + STAT_BYTES);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* row_valid = reinterpret_cast<uint8_t*>(tmem_slot + 2);  // 128 bytes
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int phase_id = blockIdx.z;
-  const int mt = blockIdx.x;
-  const int tx = mt % p.tiles_x;
-  const int ty = (mt / p.tiles_x) % p.tiles_y;
-  const int tn = mt / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
-  const int ncol0 = blockIdx.y * BN;
-
-  const int tap_begin = p.tap_start[phase_id];
-  const int tap_end = tap_begin + p.tap_count[phase_id];
-  int num_kb = 0;
-  for (int t = tap_begin; t < tap_end; ++t) num_kb += p.taps[t].nchunks;
+  const int tiles_per_phase = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_per_phase * p.phases;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
     }
-    tc::mbar_init(tmem_full_bar, 1);
+    tc::mbar_init(&tmem_full_bar[0], 1);
+    tc::mbar_init(&tmem_full_bar[1], 1);
+    tc::mbar_init(&tmem_empty_bar[0], 8);  // one arrival per epilogue warp
+    tc::mbar_init(&tmem_empty_bar[1], 8);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&p.tmB);
-    tc::prefetch_tmap(&p.tmD[phase_id]);
+    tc::prefetch_tmap(&p.tmA[0]);
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, BN);
+    tc::tmem_alloc(tmem_slot, 2 * BN);
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
@@ -147,174 +155,228 @@ __global__ void __launch_bounds__(kGemmThreads) conv_gemm_kernel(const __grid_co
     // ===================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)p.rows * A_ROW_BYTES;
-      int kb = 0;
-      for (int t = tap_begin; t < tap_end; ++t) {
-        const TapDesc tap = p.taps[t];
-        const CUtensorMap* mA = &p.tmA[tap.src];
-        for (int ch = 0; ch < tap.nchunks; ++ch, ++kb) {
-          const int s = kb % stages;
-          const uint32_t ph = (kb / stages) & 1;
-          tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
-          tc::mbar_expect_tx(&full_bar[s], a_bytes + B_BYTES);
-          tc::tma_load_4d(sa, mA, &full_bar[s], ch * BK, x0 + tap.dx, y0 + tap.dy, n0);
-          if (!B_MN) {
-            // box (BK k, BN rows, 1 tap)
-            tc::tma_load_3d(sb, &p.tmB, &full_bar[s], tap.wk0 + ch * BK, p.n_off + ncol0, tap.wtap);
-          } else {
-            // weight viewed as (cin inner = N, cout = K rows, tap): BMN_SUBS boxes of (BMN_CW, BK, 1)
+      uint32_t kb = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int mt = (t / p.n_tiles) % p.m_tiles;
+        const int phase_id = t / tiles_per_phase;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+        const int ncol0 = nt * BN;
+        const int tap_begin = p.tap_start[phase_id], tap_end = tap_begin + p.tap_count[phase_id];
+        for (int tp = tap_begin; tp < tap_end; ++tp) {
+          const TapDesc tap = p.taps[tp];
+          const CUtensorMap* mA = &p.tmA[tap.src];
+          for (int ch = 0; ch < tap.nchunks; ++ch, ++kb) {
+            const int s = kb % stages;
+            const uint32_t ph = (kb / stages) & 1;
+            tc::mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            tc::mbar_expect_tx(&full_bar[s], a_bytes + B_BYTES);
+            tc::tma_load_4d(sa, mA, &full_bar[s], ch * BK, x0 + tap.dx, y0 + tap.dy, n0);
+            if (!B_MN) {
+              tc::tma_load_3d(sb, &p.tmB, &full_bar[s], tap.wk0 + ch * BK, p.n_off + ncol0, tap.wtap);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BMN_SUBS; ++j)
-              tc::tma_load_3d(sb + j * BMN_SUB_BYTES, &p.tmB, &full_bar[s], p.n_off + ncol0 + j * BMN_CW,
-                              tap.wk0 + ch * BK, tap.wtap);
+              for (int j = 0; j < BMN_SUBS; ++j)
+                tc::tma_load_3d(sb + j * BMN_SUB_BYTES, &p.tmB, &full_bar[s], p.n_off + ncol0 + j * BMN_CW,
+                                tap.wk0 + ch * BK, tap.wtap);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % stages;
-      const uint32_t ph = (kb / stages) & 1;
-      tc::mbar_wait(&full_bar[s], ph);
+    uint32_t kb = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int phase_id = t / tiles_per_phase;
+      const int tap_begin = p.tap_start[phase_id], tap_end = tap_begin + p.tap_count[phase_id];
+      int num_kb = 0;
+      for (int tp = tap_begin; tp < tap_end; ++tp) num_kb += p.taps[tp].nchunks;
+      const int acc = it & 1;
+      tc::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       tc::tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
-        const uint64_t da0 = tc::make_smem_desc(sa, 16, 8 * A_ROW_BYTES, A_LAYOUT);
-        uint64_t db0;
-        if (!B_MN) db0 = tc::make_smem_desc(sb, 16, 8 * A_ROW_BYTES, A_LAYOUT);
-        else db0 = tc::make_smem_desc(sb, BMN_SUB_BYTES, 8 * BMN_ROW_BYTES, BMN_LAYOUT);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      for (int i = 0; i < num_kb; ++i, ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da0 = tc::make_smem_desc(sa, 16, 8 * A_ROW_BYTES, A_LAYOUT);
+          uint64_t db0;
+          if (!B_MN) db0 = tc::make_smem_desc(sb, 16, 8 * A_ROW_BYTES, A_LAYOUT);
+          else db0 = tc::make_smem_desc(sb, BMN_SUB_BYTES, 8 * BMN_ROW_BYTES, BMN_LAYOUT);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = da0 + (uint64_t)((k * 32) >> 4);
-          const uint64_t db = B_MN ? db0 + (uint64_t)((k * 16 * BMN_ROW_BYTES) >> 4) : db0 + (uint64_t)((k * 32) >> 4);
-          tc::umma_bf16(tmem_base, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = da0 + (uint64_t)((k * 32) >> 4);
+            const uint64_t db = B_MN ? db0 + (uint64_t)((k * 16 * BMN_ROW_BYTES) >> 4) : db0 + (uint64_t)((k * 32) >> 4);
+            tc::umma_bf16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&empty_bar[s]);
+          if (i == num_kb - 1) tc::umma_commit(&tmem_full_bar[acc]);
         }
-        tc::umma_commit(&empty_bar[s]);
-        if (kb == num_kb - 1) tc::umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    // ===================================================== epilogue (warps 2..9, 256 threads)
+    const int ew = warp - 2;           // 0..7
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;          // which 32-column chunks: j % 2 == half
+    const int et = threadIdx.x - 64;   // 0..255
     const int row = q * 32 + lane;
     const int wi = row % p.bw;
     const int hi = (row / p.bw) % p.bh;
     const int ni = row / (p.bw * p.bh);
-    const int ox = x0 + wi, oy = y0 + hi, on = n0 + ni;
-    const bool valid = row < p.rows && ox < p.Wv && oy < p.Hv && on < p.Nimg;
-    row_valid[row] = valid ? 1 : 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int nt = t % p.n_tiles;
+      const int mt = (t / p.n_tiles) % p.m_tiles;
+      const int phase_id = t / tiles_per_phase;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+      const int ncol0 = nt * BN;
+      const int ox = x0 + wi, oy = y0 + hi, on = n0 + ni;
+      const bool valid = row < p.rows && ox < p.Wv && oy < p.Hv && on < p.Nimg;
+      const int acc = it & 1;
 
-    const __nv_bfloat16* mrow = nullptr;
-    if (p.mask != nullptr && valid) {
-      const int fy = oy * p.mask_s + (p.mask_s == 2 ? (phase_id >> 1) : 0);
-      const int fx = ox * p.mask_s + (p.mask_s == 2 ? (phase_id & 1) : 0);
-      mrow = p.mask + (((size_t)on * p.mask_H + fy) * p.mask_W + fx) * p.mask_C + p.n_off + ncol0;
-    }
+      // the previous tile's TMA stores must have finished reading the staging buffer
+      if (et == 0) tc::tma_store_wait_read0();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) row_valid[row] = valid ? 1 : 0;
 
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::tc_fence_after();
+      const __nv_bfloat16* mrow = nullptr;
+      if (p.mask != nullptr && valid) {
+        const int fy = oy * p.mask_s + (p.mask_s == 2 ? (phase_id >> 1) : 0);
+        const int fx = ox * p.mask_s + (p.mask_s == 2 ? (phase_id & 1) : 0);
+        mrow = p.mask + (((size_t)on * p.mask_H + fy) * p.mask_W + fx) * p.mask_C + p.n_off + ncol0;
+      }
+
+      tc::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tc::tmem_ld_wait();
-      float f[32];
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_acc + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        float f[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-      if (p.bias != nullptr) {
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + p.n_off + ncol0 + c0 + i);
-      }
-      if (p.relu) {
+          for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + p.n_off + ncol0 + c0 + i);
+        }
+        if (p.relu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-      }
-      if (mrow != nullptr) {
-        const uint4* mp = reinterpret_cast<const uint4*>(mrow + c0);
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (mrow != nullptr) {
+          const uint4* mp = reinterpret_cast<const uint4*>(mrow + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 m = __ldg(mp + j);
+            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // bf16 > 0  <=>  sign bit clear and magnitude nonzero
+              const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
+              if (!(lo != 0 && lo < 0x8000u)) f[j * 8 + e * 2] = 0.f;
+              if (!(hi2 != 0 && hi2 < 0x8000u)) f[j * 8 + e * 2 + 1] = 0.f;
+            }
+          }
+        }
+        // stage as bf16 into the swizzled output tile: chunk (c0 / OUT_CW), 16-byte units within the row
+        const int chunk = c0 / OUT_CW;
+        const int unit0 = (c0 % OUT_CW) / 8;
+        uint8_t* rowp = out_stage + (size_t)chunk * OUT_CHUNK_BYTES + (size_t)row * OUT_ROW_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 m = __ldg(mp + j);
-          const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            // bf16 > 0  <=>  sign bit clear and magnitude nonzero
-            const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
-            if (!(lo != 0 && lo < 0x8000u)) f[j * 8 + e * 2] = 0.f;
-            if (!(hi2 != 0 && hi2 < 0x8000u)) f[j * 8 + e * 2 + 1] = 0.f;
-          }
+          uint4 o;
+          o.x = tc::pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+          o.y = tc::pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+          o.z = tc::pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+          o.w = tc::pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+          int unit = unit0 + j;
+          if (OUT_CW == 64) unit ^= (row & 7);          // SWIZZLE_128B
+          else unit ^= ((row >> 1) & 3);                // SWIZZLE_64B
+          *reinterpret_cast<uint4*>(rowp + unit * 16) = o;
         }
       }
-      // stage as bf16 into the swizzled output tile: chunk (c0 / OUT_CW), 16-byte units within the row
-      const int chunk = c0 / OUT_CW;
-      const int unit0 = (c0 % OUT_CW) / 8;  // first 16B unit of these 32 channels inside the row
-      uint8_t* rowp = smem + (size_t)chunk * OUT_CHUNK_BYTES + (size_t)row * OUT_ROW_BYTES;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = tc::pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-        o.y = tc::pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-        o.z = tc::pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-        o.w = tc::pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-        int unit = unit0 + j;
-        if (OUT_CW == 64) unit ^= (row & 7);          // SWIZZLE_128B
-        else unit ^= ((row >> 1) & 3);                // SWIZZLE_64B
-        *reinterpret_cast<uint4*>(rowp + unit * 16) = o;
-      }
-    }
-    tc::fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+      // this warp no longer needs the accumulator
+      tc::tc_fence_before();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+      tc::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
-    if (p.stats != nullptr) {
-      // per-channel sum / sum of squares of the bf16-rounded outputs over the valid rows of this tile
-      const int et = threadIdx.x - 64;  // 0..127
-      constexpr int GROUPS = 128 / OUT_CW;
-      constexpr int ROWS_PER_GROUP = 128 / GROUPS;
-      const int c = et % OUT_CW;
-      const int g = et / OUT_CW;
-      for (int chunk = 0; chunk < OUT_CHUNKS; ++chunk) {
-        float s1 = 0.f, s2 = 0.f;
-        const uint8_t* cb = smem + (size_t)chunk * OUT_CHUNK_BYTES;
-        for (int r = g * ROWS_PER_GROUP; r < (g + 1) * ROWS_PER_GROUP; ++r) {
-          if (row_valid[r]) {
-            int unit = c >> 3;
-            if (OUT_CW == 64) unit ^= (r & 7);
-            else unit ^= ((r >> 1) & 3);
-            const __nv_bfloat16 hv =
-                *reinterpret_cast<const __nv_bfloat16*>(cb + (size_t)r * OUT_ROW_BYTES + unit * 16 + (c & 7) * 2);
-            const float x = __bfloat162float(hv);
-            s1 += x;
-            s2 += x * x;
+      if (p.stats != nullptr) {
+        // per-channel sum / sum of squares of the STORED (bf16) values over the valid rows: 16-byte smem reads,
+        // thread = (row group, 8-channel group); row groups are combined through shared memory -> 2*BN atomics per tile
+        const int cg = et % CG, rg = et / CG;
+        const int chunk = (cg * 8) / OUT_CW;
+        const int unit_l = ((cg * 8) % OUT_CW) / 8;
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+        const uint8_t* cb = out_stage + (size_t)chunk * OUT_CHUNK_BYTES;
+#pragma unroll 4
+        for (int r = rg * ROWS_PER_RG; r < (rg + 1) * ROWS_PER_RG; ++r) {
+          if (!row_valid[r]) continue;
+          int unit = unit_l;
+          if (OUT_CW == 64) unit ^= (r & 7);
+          else unit ^= ((r >> 1) & 3);
+          const uint4 pk = *reinterpret_cast<const uint4*>(cb + (size_t)r * OUT_ROW_BYTES + unit * 16);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 xy = __bfloat1622float2(h2[j]);
+            s1[2 * j] += xy.x; s2[2 * j] += xy.x * xy.x;
+            s1[2 * j + 1] += xy.y; s2[2 * j + 1] += xy.y * xy.y;
           }
         }
-        const int ch = p.n_off + ncol0 + chunk * OUT_CW + c;
-        atomicAdd(p.stats + ch, s1);
-        atomicAdd(p.stats + p.stats_c + ch, s2);
-      }
-    }
-
-    if (warp == 2 && lane == 0) {
-      const CUtensorMap* mD = &p.tmD[phase_id];
+        float* sc = stat_scratch + ((size_t)rg * BN + cg * 8) * 2;
 #pragma unroll
-      for (int chunk = 0; chunk < OUT_CHUNKS; ++chunk) {
-        const void* src = smem + (size_t)chunk * OUT_CHUNK_BYTES;
-        if (p.accumulate) tc::tma_reduce_add_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
-        else tc::tma_store_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+        for (int j = 0; j < 8; ++j) { sc[2 * j] = s1[j]; sc[2 * j + 1] = s2[j]; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = et; c < BN; c += 256) {
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int g = 0; g < RG; ++g) {
+            a1 += stat_scratch[((size_t)g * BN + c) * 2];
+            a2 += stat_scratch[((size_t)g * BN + c) * 2 + 1];
+          }
+          const int ch = p.n_off + ncol0 + c;
+          atomicAdd(p.stats + ch, a1);
+          atomicAdd(p.stats + p.stats_c + ch, a2);
+        }
       }
-      tc::tma_store_commit();
-      tc::tma_store_wait_read0();
+
+      if (et == 0) {
+        const CUtensorMap* mD = &p.tmD[phase_id];
+#pragma unroll
+        for (int chunk = 0; chunk < OUT_CHUNKS; ++chunk) {
+          const void* src = out_stage + (size_t)chunk * OUT_CHUNK_BYTES;
+          if (p.accumulate) tc::tma_reduce_add_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+          else tc::tma_store_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+        }
+        tc::tma_store_commit();
+      }
     }
+    if (et == 0) tc::tma_store_wait_read0();
   }
 
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, BN);
+    tc::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 

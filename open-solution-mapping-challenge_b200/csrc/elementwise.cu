@@ -702,7 +702,7 @@ extern "C" int mcb_channel_sum(const void* x, float* out, long pixels, int c, vo
   int threads, c8;
   if (int r = reduce_cfg(c, &threads, &c8)) return r;
   const int lanes = threads / c8;
-  const int grid = (int)std::max(1L, std::min((pixels + lanes * 16 - 1) / (lanes * 16), (long)num_sms() * 4));
+  const int grid = (int)std::max(1L, std::min((pixels + lanes * 4 - 1) / (lanes * 4), (long)num_sms() * 4));
   channel_reduce_kernel<0><<<grid, threads, (size_t)threads * 8 * 2 * sizeof(float), ST>>>(
       (const uint4*)x, nullptr, nullptr, nullptr, nullptr, out, nullptr, pixels, c8);
   MCB_LAUNCH_CHECK();
@@ -714,7 +714,7 @@ extern "C" int mcb_bn_bwd_reduce(const void* dy, const void* y_mask, const void*
   int threads, c8;
   if (int r = reduce_cfg(c, &threads, &c8)) return r;
   const int lanes = threads / c8;
-  const int grid = (int)std::max(1L, std::min((pixels + lanes * 16 - 1) / (lanes * 16), (long)num_sms() * 4));
+  const int grid = (int)std::max(1L, std::min((pixels + lanes * 4 - 1) / (lanes * 4), (long)num_sms() * 4));
   channel_reduce_kernel<1><<<grid, threads, (size_t)threads * 8 * 2 * sizeof(float), ST>>>(
       (const uint4*)dy, (const uint4*)y_mask, (const uint4*)z, mean, invstd, dbeta, dgamma, pixels, c8);
   MCB_LAUNCH_CHECK();

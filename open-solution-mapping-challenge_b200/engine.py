@@ -54,6 +54,7 @@ class Plan:
         self._keep = []            # keeps tensors referenced by closures alive
         self._bns = []
         self._bwd_builders = []    # one per forward unit; run in REVERSE so store/accumulate modes follow run order
+        self.units = []            # (kind, state_dict prefix, inputs, output) per forward unit, for per-unit parity tests
         total_c = sum(m.num_features for m in net.modules() if isinstance(m, nn.BatchNorm2d))
         self._stats_arena = torch.zeros(2 * total_c, dtype=F32, device=self.dev)
         self._stats_used = 0
@@ -227,9 +228,11 @@ class Plan:
         # ---- encoder stages (torchvision BasicBlock / Bottleneck)
         x = c1
         skips = []
-        for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
-            for blk in layer:
+        for li, layer in enumerate((enc.layer1, enc.layer2, enc.layer3, enc.layer4)):
+            for bi, blk in enumerate(layer):
+                xin = x
                 x = self._res_block(x, blk)
+                self.units.append(("block", "encoder.layer%d.%d" % (li + 1, bi), (xin,), x))
             skips.append(x)
         c2, c3, c4, c5 = skips
 
@@ -248,6 +251,9 @@ class Plan:
         d3 = self._decoder(d4, c3, net.dec3)
         d2 = self._decoder(d3, c2, net.dec2)
         d1 = self._decoder(d2, None, net.dec1)
+        self.units += [("decoder", "center", (pool,), center), ("decoder", "dec5", (center, c5), d5),
+                       ("decoder", "dec4", (d5, c4), d4), ("decoder", "dec3", (d4, c3), d3),
+                       ("decoder", "dec2", (d3, c2), d2), ("decoder", "dec1", (d2,), d1)]
         # dec0 = ConvRelu(32, 32)
         conv0 = net.dec0.conv
         w0_16 = net._packed(conv0.weight, net._w16)

@@ -158,7 +158,7 @@ def test_batchnorm_train_forward_backward(mcb, cuda, c, n, h, w, residual):
 
 def test_batchnorm_eval_params(mcb, cuda):
     from mcb200 import ops
-    c = 96
+    c = 128
     g = torch.Generator().manual_seed(1)
     gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
     rm, rv = torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.2
