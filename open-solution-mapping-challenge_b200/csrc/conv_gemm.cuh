@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t a_bytes = (uint32_t)p.rows * A_ROW_BYTES;
       uint32_t kb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles;
-        const int mt = (t / p.n_tiles) % p.m_tiles;
-        const int phase_id = t / tiles_per_phase;
+        const int phase_id = t % p.phases;  // phases of one pixel tile run together: they share the A tile in L2
+        const int nt = (t / p.phases) % p.n_tiles;
+        const int mt = t / (p.phases * p.n_tiles);
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
         const int ncol0 = nt * BN;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     uint32_t kb = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int phase_id = t / tiles_per_phase;
+      const int phase_id = t % p.phases;
       const int tap_begin = p.tap_start[phase_id], tap_end = tap_begin + p.tap_count[phase_id];
       int num_kb = 0;
       for (int tp = tap_begin; tp < tap_end; ++tp) num_kb += p.taps[tp].nchunks;
@@ -236,9 +236,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int ni = row / (p.bw * p.bh);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int nt = t % p.n_tiles;
-      const int mt = (t / p.n_tiles) % p.m_tiles;
-      const int phase_id = t / tiles_per_phase;
+      const int phase_id = t % p.phases;
+      const int nt = (t / p.phases) % p.n_tiles;
+      const int mt = t / (p.phases * p.n_tiles);
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
       const int ncol0 = nt * BN;
