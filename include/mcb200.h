@@ -66,6 +66,14 @@ typedef struct {
   const void* relu_mask; /* NHWC bf16 like dx or NULL: dx is zeroed where relu_mask <= 0 (backward of the ReLU that
                             produced the conv input) */
   int accumulate;        /* dx += (TMA reduce-add) instead of dx = */
+  /* optional fused BatchNorm-backward reductions for the BN whose ReLU output is this conv's input (dx is then
+     g = dy_in * (relu_mask > 0)):  bn_dbeta[c] += sum g,  bn_dgamma[c] += sum g * (bn_z - bn_mean[c]) * bn_invstd[c];
+     bn_z: NHWC bf16 like dx (the BN input); all NULL to disable */
+  const void* bn_z;
+  const float* bn_mean;
+  const float* bn_invstd;
+  float* bn_dbeta;
+  float* bn_dgamma;
 } mcb_conv_dgrad_args;
 int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream);
 

@@ -24,7 +24,8 @@ class ConvFwdArgs(C.Structure):
 class ConvDgradArgs(C.Structure):
     _fields_ = [("dy", vp), ("n", ci), ("h", ci), ("w", ci), ("weight", vp), ("cout", ci), ("cin_total", ci),
                 ("ci_off", ci), ("cin", ci), ("ksize", ci), ("stride", ci), ("dx", vp), ("relu_mask", vp),
-                ("accumulate", ci)]
+                ("accumulate", ci), ("bn_z", vp), ("bn_mean", vp), ("bn_invstd", vp), ("bn_dbeta", vp),
+                ("bn_dgamma", vp)]
 
 
 class ConvWgradArgs(C.Structure):

@@ -70,7 +70,7 @@ static int launch_conv(int BN, int BK, bool b_mn, ConvGemmParams& p, int m_tiles
   const int stage = a_bytes + b_bytes;
   const int out_bytes = 128 * BN * 2;
   const int stat_bytes = 16 * 1024;  // (2048 / BN row groups) x BN columns x {sum, sumsq} floats == 16 KB for every BN
-  const int fixed = out_bytes + stat_bytes + 1024 /*align*/ + 512 /*barriers*/;
+  const int fixed = out_bytes + stat_bytes + 1024 /*align*/ + 1536 /*barriers, row tables*/;
   const int budget = std::min(env_int("MCB_SMEM_BUDGET_KB", 227) * 1024, 232448);
   int stages = std::max(2, std::min(env_int("MCB_MAX_STAGES", 6), (budget - fixed) / stage));
   p.stages = stages;
@@ -290,9 +290,16 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
                                  out_cw * 2)) return r;
   }
   p.accumulate = a->accumulate;
-  if (a->relu_mask) {
+  if (a->relu_mask || a->bn_z) {
     p.mask = static_cast<const __nv_bfloat16*>(a->relu_mask);
     p.mask_H = H; p.mask_W = W; p.mask_C = a->cin; p.mask_s = a->stride;
+  }
+  if (a->bn_z) {
+    MCB_REQUIRE(a->bn_mean && a->bn_invstd && a->bn_dbeta && a->bn_dgamma, "conv_dgrad: incomplete bn reduction args");
+    MCB_REQUIRE(!a->accumulate, "conv_dgrad: bn reduction needs the complete gradient (no accumulate)");
+    MCB_REQUIRE(!(a->stride == 2 && a->ksize == 1), "conv_dgrad: bn reduction with a 1x1 stride-2 conv is unsupported");
+    p.bn_z = static_cast<const __nv_bfloat16*>(a->bn_z);
+    p.bn_mean = a->bn_mean; p.bn_invstd = a->bn_invstd; p.bn_dbeta = a->bn_dbeta; p.bn_dgamma = a->bn_dgamma;
   }
   return launch_conv(BN, BK, true, p, (int)m_tiles, a->cin / BN, phases, st);
 }

@@ -50,6 +50,13 @@ struct ConvGemmParams {
   int mask_H, mask_W, mask_C, mask_s;  // full dims; mask_s = 1 (plain) or 2 (output is a parity view)
   int relu;
   int accumulate;
+  // fused BatchNorm-backward reductions (dgrad only): with g = the stored (masked) output gradient,
+  // dbeta += sum g, dgamma += sum g * (z - mean) * invstd; z has the geometry of `mask`
+  const __nv_bfloat16* bn_z;
+  const float* bn_mean;
+  const float* bn_invstd;
+  float* bn_dbeta;
+  float* bn_dgamma;
 };
 
 struct WgradTap {
@@ -107,10 +114,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   constexpr int OUT_CHUNKS = BN / OUT_CW;
   constexpr int OUT_BYTES = OUT_CHUNKS * OUT_CHUNK_BYTES;
   // statistics scratch: RG row groups x BN columns x {sum, sumsq}
-  constexpr int CG = BN / 8;            // column groups of 8 channels
-  constexpr int RG = 256 / CG;          // row groups (256 epilogue threads)
-  constexpr int ROWS_PER_RG = 128 / RG;
-  constexpr int STAT_BYTES = RG * BN * 2 * 4;
+  constexpr int STAT_BYTES = 2 * 8192;  // per half: (128 / (OUT_CW/8)) row groups x OUT_CW columns x {a, b} floats
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_up_1024(smem_raw);
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* row_valid = reinterpret_cast<uint8_t*>(tmem_slot + 2);  // 128 bytes
+  int* row_pix = reinterpret_cast<int*>(tmem_slot + 2);  // [2][128] pixel index in the full-resolution tensor, -1 = invalid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,9 +161,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t a_bytes = (uint32_t)p.rows * A_ROW_BYTES;
       uint32_t kb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int phase_id = t % p.phases;  // phases of one pixel tile run together: they share the A tile in L2
-        const int nt = (t / p.phases) % p.n_tiles;
-        const int mt = t / (p.phases * p.n_tiles);
+        // tile order: phase fastest (the phases of one pixel tile share the A tile in L2), then pixel tile, N tile
+        // slowest (CTAs running together share the weight tile; a CTA keeps its N tile for many tiles in a row)
+        const int phase_id = t % p.phases;
+        const int mt = (t / p.phases) % p.m_tiles;
+        const int nt = t / (p.phases * p.m_tiles);
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
         const int ncol0 = nt * BN;
@@ -225,151 +231,244 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..9, 256 threads)
+    // ===================================================== epilogue (warps 2..9 = two halves of 128 threads)
+    // Each half (4 warps = the 4 TMEM lane quadrants = all 128 rows) owns whole OUT_CW-column chunks: half h takes
+    // chunks h, h+2, ...  Per chunk: wait until the TMA store that last used this chunk's staging buffer has read it,
+    // TMEM -> registers -> bias/ReLU/mask -> bf16 -> swizzled smem, per-channel reductions from smem, TMA store.
+    // The two halves never synchronise with each other; stores of one chunk overlap the math of the next.
     const int ew = warp - 2;           // 0..7
     const int q = warp & 3;            // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;          // which 32-column chunks: j % 2 == half
-    const int et = threadIdx.x - 64;   // 0..255
+    const int half = ew >> 2;
+    const int eth = (threadIdx.x - 64) & 127;  // thread index inside the half
+    const int bar_id = 2 + half;
+    constexpr int CH = (OUT_CHUNKS + 1) / 2;   // chunks per half (half 1 may own fewer)
+    constexpr int CGc = OUT_CW / 8;            // 8-channel groups per chunk
+    constexpr int RGc = 128 / CGc;             // row groups
+    constexpr int ROWSc = 128 / RGc;           // rows per thread in the reduction
+    int* my_row_pix = row_pix + half * 128;
+    float* my_scratch = stat_scratch + half * (RGc * OUT_CW * 2);
     const int row = q * 32 + lane;
     const int wi = row % p.bw;
     const int hi = (row / p.bw) % p.bh;
     const int ni = row / (p.bw * p.bh);
+    const int my_chunks = (OUT_CHUNKS > half) ? (OUT_CHUNKS - half + 1) / 2 : 0;
+    // per-channel reductions are kept in registers (threads eth < OUT_CW, one channel per chunk) across all tiles of
+    // this CTA that share an N tile, and flushed with one atomic per channel when the N tile changes / at the end
+    float racc1[CH], racc2[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) racc1[j] = racc2[j] = 0.f;
+    int racc_nt = -1;
+    const bool do_red = (p.stats != nullptr || p.bn_z != nullptr);
+    auto flush_reductions = [&]() {
+      if (racc_nt >= 0 && eth < OUT_CW) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          if (j < my_chunks) {
+            const int ch = p.n_off + racc_nt * BN + (half + 2 * j) * OUT_CW + eth;
+            if (p.bn_z == nullptr) {
+              atomicAdd(p.stats + ch, racc1[j]);
+              atomicAdd(p.stats + p.stats_c + ch, racc2[j]);
+            } else {
+              atomicAdd(p.bn_dbeta + ch, racc1[j]);
+              atomicAdd(p.bn_dgamma + ch, racc2[j]);
+            }
+            racc1[j] = racc2[j] = 0.f;
+          }
+        }
+      }
+    };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int phase_id = t % p.phases;
-      const int nt = (t / p.phases) % p.n_tiles;
-      const int mt = t / (p.phases * p.n_tiles);
+      const int mt = (t / p.phases) % p.m_tiles;
+      const int nt = t / (p.phases * p.m_tiles);
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
       const int ncol0 = nt * BN;
       const int ox = x0 + wi, oy = y0 + hi, on = n0 + ni;
       const bool valid = row < p.rows && ox < p.Wv && oy < p.Hv && on < p.Nimg;
       const int acc = it & 1;
-
-      // the previous tile's TMA stores must have finished reading the staging buffer
-      if (et == 0) tc::tma_store_wait_read0();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0) row_valid[row] = valid ? 1 : 0;
-
-      const __nv_bfloat16* mrow = nullptr;
-      if (p.mask != nullptr && valid) {
-        const int fy = oy * p.mask_s + (p.mask_s == 2 ? (phase_id >> 1) : 0);
-        const int fx = ox * p.mask_s + (p.mask_s == 2 ? (phase_id & 1) : 0);
-        mrow = p.mask + (((size_t)on * p.mask_H + fy) * p.mask_W + fx) * p.mask_C + p.n_off + ncol0;
+      if (do_red && nt != racc_nt) {
+        flush_reductions();
+        racc_nt = nt;
       }
+      int pix = -1;
+      if (valid) {
+        pix = 0;
+        if (p.mask_H > 0) {
+          const int fy = oy * p.mask_s + (p.mask_s == 2 ? (phase_id >> 1) : 0);
+          const int fx = ox * p.mask_s + (p.mask_s == 2 ? (phase_id & 1) : 0);
+          pix = (on * p.mask_H + fy) * p.mask_W + fx;
+        }
+      }
+      const __nv_bfloat16* mrow = nullptr;
+      if (p.mask != nullptr && valid) mrow = p.mask + (size_t)pix * p.mask_C + p.n_off + ncol0;
 
       tc::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
       tc::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 
-#pragma unroll 1
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_acc + (uint32_t)c0, v);
-        tc::tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + p.n_off + ncol0 + c0 + i);
+      for (int cj = 0; cj < my_chunks; ++cj) {
+        const int chunk = half + 2 * cj;
+        uint8_t* cbuf = out_stage + (size_t)chunk * OUT_CHUNK_BYTES;
+        // the store that used this buffer one tile ago must have finished reading it (bulk groups retire in order)
+        if (eth == 0) {
+          if (CH <= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        if (p.relu) {
+        if (cj == 0) my_row_pix[row] = pix;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (mrow != nullptr) {
-          const uint4* mp = reinterpret_cast<const uint4*>(mrow + c0);
+        for (int sub = 0; sub < OUT_CW / 32; ++sub) {
+          const int c0 = chunk * OUT_CW + sub * 32;
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tmem_acc + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 m = __ldg(mp + j);
-            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + p.n_off + ncol0 + c0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // bf16 > 0  <=>  sign bit clear and magnitude nonzero
-              const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
-              if (!(lo != 0 && lo < 0x8000u)) f[j * 8 + e * 2] = 0.f;
-              if (!(hi2 != 0 && hi2 < 0x8000u)) f[j * 8 + e * 2 + 1] = 0.f;
+            for (int i = 0; i < 8; ++i) {
+              const float4 bv = __ldg(bp + i);
+              f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
             }
           }
-        }
-        // stage as bf16 into the swizzled output tile: chunk (c0 / OUT_CW), 16-byte units within the row
-        const int chunk = c0 / OUT_CW;
-        const int unit0 = (c0 % OUT_CW) / 8;
-        uint8_t* rowp = out_stage + (size_t)chunk * OUT_CHUNK_BYTES + (size_t)row * OUT_ROW_BYTES;
+          if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = tc::pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-          o.y = tc::pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-          o.z = tc::pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-          o.w = tc::pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-          int unit = unit0 + j;
-          if (OUT_CW == 64) unit ^= (row & 7);          // SWIZZLE_128B
-          else unit ^= ((row >> 1) & 3);                // SWIZZLE_64B
-          *reinterpret_cast<uint4*>(rowp + unit * 16) = o;
-        }
-      }
-      // this warp no longer needs the accumulator
-      tc::tc_fence_before();
-      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
-      tc::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-
-      if (p.stats != nullptr) {
-        // per-channel sum / sum of squares of the STORED (bf16) values over the valid rows: 16-byte smem reads,
-        // thread = (row group, 8-channel group); row groups are combined through shared memory -> 2*BN atomics per tile
-        const int cg = et % CG, rg = et / CG;
-        const int chunk = (cg * 8) / OUT_CW;
-        const int unit_l = ((cg * 8) % OUT_CW) / 8;
-        float s1[8], s2[8];
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (mrow != nullptr) {
+            const uint4* mp = reinterpret_cast<const uint4*>(mrow + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-        const uint8_t* cb = out_stage + (size_t)chunk * OUT_CHUNK_BYTES;
-#pragma unroll 4
-        for (int r = rg * ROWS_PER_RG; r < (rg + 1) * ROWS_PER_RG; ++r) {
-          if (!row_valid[r]) continue;
-          int unit = unit_l;
-          if (OUT_CW == 64) unit ^= (r & 7);
-          else unit ^= ((r >> 1) & 3);
-          const uint4 pk = *reinterpret_cast<const uint4*>(cb + (size_t)r * OUT_ROW_BYTES + unit * 16);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            for (int j = 0; j < 4; ++j) {
+              const uint4 m = __ldg(mp + j);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // bf16 > 0  <=>  sign bit clear and magnitude nonzero
+                const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
+                if (!(lo != 0 && lo < 0x8000u)) f[j * 8 + e * 2] = 0.f;
+                if (!(hi2 != 0 && hi2 < 0x8000u)) f[j * 8 + e * 2 + 1] = 0.f;
+              }
+            }
+          }
+          uint8_t* rowp = cbuf + (size_t)row * OUT_ROW_BYTES;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 xy = __bfloat1622float2(h2[j]);
-            s1[2 * j] += xy.x; s2[2 * j] += xy.x * xy.x;
-            s1[2 * j + 1] += xy.y; s2[2 * j + 1] += xy.y * xy.y;
+            uint4 o;
+            o.x = tc::pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+            o.y = tc::pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+            o.z = tc::pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+            o.w = tc::pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+            int unit = sub * 4 + j;
+            if (OUT_CW == 64) unit ^= (row & 7);          // SWIZZLE_128B
+            else unit ^= ((row >> 1) & 3);                // SWIZZLE_64B
+            *reinterpret_cast<uint4*>(rowp + unit * 16) = o;
           }
         }
-        float* sc = stat_scratch + ((size_t)rg * BN + cg * 8) * 2;
+        if (cj == my_chunks - 1) {
+          // this warp is done with the accumulator
+          tc::tc_fence_before();
+          if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        tc::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+
+        if (p.stats != nullptr || p.bn_z != nullptr) {
+          // Per-channel reductions over the valid rows of the STORED (bf16) chunk: 16-byte smem reads,
+          // thread = (row group, 8-channel group); row groups are combined through shared memory.
+          //   forward: (sum v, sum v^2)       -> BatchNorm batch statistics of the following layer
+          //   dgrad:   (sum g, sum g * xhat)  -> dbeta / dgamma of the BatchNorm that produced this conv's input
+          const bool bnred = p.bn_z != nullptr;
+          const int cg = eth % CGc, rg = eth / CGc;
+          const int ch0 = p.n_off + ncol0 + chunk * OUT_CW + cg * 8;
+          float s1[8], s2[8], mu[8], is[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[2 * j] = s1[j]; sc[2 * j + 1] = s2[j]; }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int c = et; c < BN; c += 256) {
-          float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-          for (int g = 0; g < RG; ++g) {
-            a1 += stat_scratch[((size_t)g * BN + c) * 2];
-            a2 += stat_scratch[((size_t)g * BN + c) * 2 + 1];
+          for (int j = 0; j < 8; ++j) {
+            s1[j] = s2[j] = 0.f;
+            mu[j] = bnred ? __ldg(p.bn_mean + ch0 + j) : 0.f;
+            is[j] = bnred ? __ldg(p.bn_invstd + ch0 + j) : 0.f;
           }
-          const int ch = p.n_off + ncol0 + c;
-          atomicAdd(p.stats + ch, a1);
-          atomicAdd(p.stats + p.stats_c + ch, a2);
+#pragma unroll
+          for (int rr = 0; rr < ROWSc; ++rr) {
+            const int r = rg * ROWSc + rr;
+            const int rp = my_row_pix[r];
+            if (rp < 0) continue;
+            int unit = cg;
+            if (OUT_CW == 64) unit ^= (r & 7);
+            else unit ^= ((r >> 1) & 3);
+            const uint4 pk = *reinterpret_cast<const uint4*>(cbuf + (size_t)r * OUT_ROW_BYTES + unit * 16);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+            if (!bnred) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 xy = __bfloat1622float2(h2[j]);
+                s1[2 * j] += xy.x; s2[2 * j] += xy.x * xy.x;
+                s1[2 * j + 1] += xy.y; s2[2 * j + 1] += xy.y * xy.y;
+              }
+            } else {
+              const uint4 zk = __ldg(reinterpret_cast<const uint4*>(p.bn_z + (size_t)rp * p.mask_C + ch0));
+              const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 g = __bfloat1622float2(h2[j]);
+                const float2 zz = __bfloat1622float2(z2[j]);
+                s1[2 * j] += g.x; s2[2 * j] += g.x * ((zz.x - mu[2 * j]) * is[2 * j]);
+                s1[2 * j + 1] += g.y; s2[2 * j + 1] += g.y * ((zz.y - mu[2 * j + 1]) * is[2 * j + 1]);
+              }
+            }
+          }
+          // combine the row groups of this warp with shuffles (lanes l, l+CGc, ... share a channel group), then the
+          // four warps through a small shared-memory table
+#pragma unroll
+          for (int off = CGc; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+              s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+            }
+          }
+          const int wq = eth >> 5;  // warp inside the half
+          if (lane < CGc) {
+            float4* sc = reinterpret_cast<float4*>(my_scratch + ((size_t)wq * CGc + lane) * 16);
+            sc[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
+            sc[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
+            sc[2] = make_float4(s1[4], s2[4], s1[5], s2[5]);
+            sc[3] = make_float4(s1[6], s2[6], s1[7], s2[7]);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (eth < OUT_CW) {
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+              const float2 v2 = *reinterpret_cast<const float2*>(my_scratch + ((size_t)w4 * CGc + (eth >> 3)) * 16 + (eth & 7) * 2);
+              a1 += v2.x;
+              a2 += v2.y;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (j == cj) { racc1[j] += a1; racc2[j] += a2; }
+          }
+        }
+
+        if (eth == 0) {
+          const CUtensorMap* mD = &p.tmD[phase_id];
+          if (p.accumulate) tc::tma_reduce_add_4d(mD, cbuf, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+          else tc::tma_store_4d(mD, cbuf, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
+          tc::tma_store_commit();
         }
       }
-
-      if (et == 0) {
-        const CUtensorMap* mD = &p.tmD[phase_id];
-#pragma unroll
-        for (int chunk = 0; chunk < OUT_CHUNKS; ++chunk) {
-          const void* src = out_stage + (size_t)chunk * OUT_CHUNK_BYTES;
-          if (p.accumulate) tc::tma_reduce_add_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
-          else tc::tma_store_4d(mD, src, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
-        }
-        tc::tma_store_commit();
+      if (my_chunks == 0) {
+        // nothing to drain for this half (BN <= 64), but stay in lock-step with the accumulator hand-off
+        tc::tc_fence_before();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
-    if (et == 0) tc::tma_store_wait_read0();
+    if (do_red) flush_reductions();
+    if (eth == 0) tc::tma_store_wait_read0();
   }
 
   tc::tc_fence_before();

@@ -146,7 +146,7 @@ class Plan:
         else:
             F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual), 0, _nb(z, y, residual))
 
-    def conv_unit_backward(self, B, dy, ymask, z, bn, conv, x, g_out=None, g_out_acc=False):
+    def conv_unit_backward(self, B, dy, ymask, z, bn, conv, x, g_out=None, g_out_acc=False, reduced=False):
         """backward of y = relu(bn(conv(x)) [+ r]) given dy = dL/dy: BN reductions + dz, wgrad, dgrad into grad(x).
         g_out receives g = dy*(y>0) for a residual branch."""
         net = self.net
@@ -154,8 +154,9 @@ class Plan:
         dz = self.act(*z.shape)
         w16 = net._packed(conv.weight, net._w16)
         gw = net._packed(conv.weight, net._g32)
-        B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma), 0,
-              _nb(dy, ymask, z))
+        if not reduced:  # else: the dgrad that produced dy already accumulated dbeta / dgamma in its epilogue
+            B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma),
+                  0, _nb(dy, ymask, z))
         B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma,
                                                       dz, g_out, g_out_acc), 0, _nb(dy, ymask, z, dz, g_out))
         desc = "%d->%d k%d s%d @%dx%dx%d" % (x.shape[3], dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2])
@@ -163,8 +164,8 @@ class Plan:
               _nb(dz, x, gw), desc)
         return dz
 
-    def dgrad_into(self, B, dz, conv, x, relu_mask=None, ci_off=0):
-        """grad(x) (+)= dgrad(dz)"""
+    def dgrad_into(self, B, dz, conv, x, relu_mask=None, ci_off=0, bn_reduce=None):
+        """grad(x) (+)= dgrad(dz); bn_reduce = (z, bn): fuse that BatchNorm's backward reductions into the epilogue"""
         net = self.net
         k, s = conv.kernel_size[0], conv.stride[0]
         w16 = net._packed(conv.weight, net._w16)
@@ -174,8 +175,13 @@ class Plan:
         cin = x.shape[3]
         if acc and relu_mask is not None:
             raise RuntimeError("plan error: masked dgrad cannot accumulate")
+        red = None
+        if bn_reduce is not None:
+            zz, bb = bn_reduce
+            red = (zz, bb.mean, bb.invstd, bb.dbeta, bb.dgamma)
         B.add("conv_dgrad", lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
-                                                   accumulate=acc, out=gx), 2.0 * dz.numel() * cin * k * k,
+                                                   accumulate=acc, out=gx, bn_reduce=red),
+              2.0 * dz.numel() * cin * k * k,
               _nb(dz, gx, relu_mask) + (_nb(gx) if acc else 0) + 2.0 * k * k * dz.shape[3] * cin,
               "%d<-%d k%d s%d @%dx%dx%d%s" % (cin, dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2],
                                               " acc" if acc else ""))
@@ -318,8 +324,9 @@ class Plan:
                 dz = dz_l
                 conv_next = conv_l
                 for conv, xin, y, z, bn in reversed(units):
-                    self.dgrad_into(B, dz, conv_next, y)
-                    dz = self.conv_unit_backward(B, self.gbuf(y), y, z, bn, conv, xin)
+                    # y has a single consumer: its ReLU mask and its BN's backward reductions ride in the dgrad epilogue
+                    self.dgrad_into(B, dz, conv_next, y, relu_mask=y, bn_reduce=(z, bn))
+                    dz = self.conv_unit_backward(B, self.gbuf(y), None, z, bn, conv, xin, reduced=True)
                     conv_next = conv
                 self.dgrad_into(B, dz, conv_next, x)
                 if blk.downsample is not None:

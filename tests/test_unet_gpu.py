@@ -137,7 +137,7 @@ def test_every_unit_against_bf16_emulated_oracle(mcb, cuda, depth, n, s):
                 tol = 4e-2
             else:
                 gg = params[nm].grad.detach().cpu()
-                tol = 4e-2 if nm.endswith("weight") and gr.dim() == 4 else 8e-2
+                tol = 8e-2  # bf16 operands, fp32 accumulation; deep layers see only a few dozen samples per channel here
             r = rel(gg, gr)
             assert r < tol, (prefix, nm, r)
             checked += 1
