@@ -52,6 +52,9 @@ typedef struct {
   float* stats;       /* fp32 [2*cout] or NULL: += per-channel sum / sum of squares of the stored (bf16) outputs:
                          the BatchNorm batch statistics of the layer that follows */
   void* y;            /* NHWC bf16 [n][h/stride][w/stride][cout] */
+  /* inference-mode BatchNorm / residual folded into the epilogue: y = relu?(acc*scale[c] + bias[c] + residual) */
+  const float* scale;   /* fp32 [cout] or NULL */
+  const void* residual; /* NHWC bf16 like y, or NULL */
 } mcb_conv_fwd_args;
 int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream);
 
@@ -233,6 +236,10 @@ int mcb_add_dropped_objects(const uint8_t* original, const uint8_t* processed, u
  * offsets int32 [planes] (exclusive prefix of the per-plane label counts); sums/counts/scores sized total_instances */
 int mcb_instance_scores(const int* labels, const void* prob, int prob_is_f64, const int* offsets, double* sums,
                         int* counts, double* scores, int total_instances, int planes, int h, int w, void* stream);
+/* same, without a host round trip: one CTA per plane, scores written at scores[plane*kcap + l - 1] for
+ * l <= min(counts[plane], kcap); counts = labels per plane (from mcb_ccl_label); workspaces sized planes*kcap */
+int mcb_instance_scores_strided(const int* labels, const void* prob, int prob_is_f64, const int* counts, double* scores,
+                                double* gsum_ws, int* gcnt_ws, int kcap, int planes, int h, int w, void* stream);
 
 /* dense_crf (src/postprocessing.py:183-225 -> pydensecrf DenseCRF2D: unary_from_softmax, addPairwiseGaussian,
  * addPairwiseBilateral, inference(iterations)); 2 labels, Potts compatibility, symmetric normalisation, Gaussian

@@ -18,7 +18,8 @@ vp, ci, fp = C.c_void_p, C.c_int, C.POINTER(C.c_float)
 
 class ConvFwdArgs(C.Structure):
     _fields_ = [("x", vp * 2), ("cin", ci * 2), ("n", ci), ("h", ci), ("w", ci), ("weight", vp), ("cout", ci),
-                ("ksize", ci), ("stride", ci), ("bias", vp), ("relu", ci), ("stats", vp), ("y", vp)]
+                ("ksize", ci), ("stride", ci), ("bias", vp), ("relu", ci), ("stats", vp), ("y", vp), ("scale", vp),
+                ("residual", vp)]
 
 
 class ConvDgradArgs(C.Structure):
@@ -149,3 +150,9 @@ class BNTrain(C.Structure):
 
 lib.mcb_bn_train_apply.argtypes = [vp, C.POINTER(BNTrain), vp, C.POINTER(BNTrain), ci, vp, cl, ci, cf, cf, vp]
 lib.mcb_bn_train_apply.restype = ci
+
+lib.mcb_bn_eval_params_batched.argtypes = [vp, ci, ci, cf, vp]
+lib.mcb_bn_eval_params_batched.restype = ci
+
+lib.mcb_instance_scores_strided.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+lib.mcb_instance_scores_strided.restype = ci

@@ -208,6 +208,11 @@ extern "C" int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream) {
   if (int r = encode_nhwc_view(&p.tmD[0], a->y, N, Ho, Wo, a->cout, 0, a->cout, -1, -1, out_cw, p.bw, p.bh, p.bn,
                                out_cw * 2)) return r;
   p.bias = a->bias; p.relu = a->relu; p.stats = a->stats; p.stats_c = a->cout;
+  p.scale = a->scale;
+  if (a->residual) {
+    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+    p.mask_H = Ho; p.mask_W = Wo; p.mask_C = a->cout; p.mask_s = 1;
+  }
   return launch_conv(BN, BK, false, p, (int)m_tiles, a->cout / BN, 1, st);
 }
 

@@ -42,7 +42,9 @@ struct ConvGemmParams {
   int m_tiles, n_tiles, phases;  // persistent tile space: phases x m_tiles x n_tiles
   int stages;
   int n_off;  // first N (weight row / column) coordinate of this launch (concat source slice for dgrad)
-  // epilogue
+  // epilogue:  v = acc * scale[c] + bias[c] + residual[pix][c];  v = relu(v);  v = mask ? v : 0
+  const float* scale;              // per-channel multiplier (inference-mode BatchNorm folded into the epilogue), or null
+  const __nv_bfloat16* residual;   // NHWC bf16 with the geometry of the output tensor (mask_H/W/C), or null
   const float* bias;
   float* stats;
   int stats_c;  // number of channels in stats (cout)
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
       const __nv_bfloat16* mrow = nullptr;
       if (p.mask != nullptr && valid) mrow = p.mask + (size_t)pix * p.mask_C + p.n_off + ncol0;
+      const __nv_bfloat16* rrow = nullptr;
+      if (p.residual != nullptr && valid) rrow = p.residual + (size_t)pix * p.mask_C + p.n_off + ncol0;
 
       tc::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
       tc::tc_fence_after();
@@ -328,12 +332,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.scale != nullptr) {
+            const float4* sp = reinterpret_cast<const float4*>(p.scale + p.n_off + ncol0 + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 sv = __ldg(sp + i);
+              f[4 * i] *= sv.x; f[4 * i + 1] *= sv.y; f[4 * i + 2] *= sv.z; f[4 * i + 3] *= sv.w;
+            }
+          }
           if (p.bias != nullptr) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + p.n_off + ncol0 + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 bv = __ldg(bp + i);
               f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
+            }
+          }
+          if (rrow != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(rrow + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rv = __ldg(rp + j);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 xy = __bfloat1622float2(r2[e]);
+                f[j * 8 + e * 2] += xy.x;
+                f[j * 8 + e * 2 + 1] += xy.y;
+              }
             }
           }
           if (p.relu) {

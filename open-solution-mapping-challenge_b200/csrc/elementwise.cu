@@ -139,6 +139,24 @@ __global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const flo
   shift[c] = beta[c] - rm[c] * sc;
 }
 
+// every BatchNorm of the net in one launch (inference): table rows = {gamma, beta, running_mean, running_var, scale,
+// shift, C} as 64-bit values; blockIdx.y = BN index
+__global__ void bn_eval_params_batched_kernel(const long long* __restrict__ table, float eps) {
+  const long long* row = table + (long long)blockIdx.y * 7;
+  const float* gamma = reinterpret_cast<const float*>(row[0]);
+  const float* beta = reinterpret_cast<const float*>(row[1]);
+  const float* rm = reinterpret_cast<const float*>(row[2]);
+  const float* rv = reinterpret_cast<const float*>(row[3]);
+  float* scale = reinterpret_cast<float*>(row[4]);
+  float* shift = reinterpret_cast<float*>(row[5]);
+  const int C = (int)row[6];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - rm[c] * sc;
+  }
+}
+
 // y = [relu]( z*scale + shift  [+ r*rscale + rshift | + r] )
 // The grid stride is a multiple of C/8, so every thread keeps ONE channel group for its whole loop and the per-channel
 // coefficients live in registers; two independent 16-byte loads per stream are in flight per iteration.
@@ -643,6 +661,13 @@ extern "C" int mcb_bn_eval_params(const float* gamma, const float* beta, const f
                                   void* stream) {
   MCB_REQUIRE(gamma && beta && running_mean && running_var && scale && shift, "bn_eval_params: null pointer");
   bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, ST>>>(gamma, beta, running_mean, running_var, eps, scale, shift, c);
+  MCB_LAUNCH_CHECK();
+  return MCB_OK;
+}
+extern "C" int mcb_bn_eval_params_batched(const long long* table, int n_bn, int max_c, float eps, void* stream) {
+  MCB_REQUIRE(table && n_bn > 0 && max_c > 0, "bn_eval_params_batched: bad arguments");
+  dim3 grid((max_c + 255) / 256, n_bn);
+  bn_eval_params_batched_kernel<<<grid, 256, 0, ST>>>(table, eps);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

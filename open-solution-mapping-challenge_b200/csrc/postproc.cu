@@ -104,31 +104,44 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     a = old;
   }
 }
-template <typename T>
-__global__ void ccl_init_kernel(const T* __restrict__ mask, int* __restrict__ L, long hw) {
-  const long base = (long)blockIdx.y * hw;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < hw; i += (long)gridDim.x * blockDim.x)
-    L[base + i] = mask[base + i] != 0 ? (int)i : -1;
-}
-__global__ void ccl_merge_kernel(int* __restrict__ L, int H, int W) {
+// One CTA (1024 threads) per plane runs the whole labelling; the phases are separated by __syncthreads():
+//   1. rows    every horizontal run gets the linear index of its first pixel (no atomics)
+//   2. merge   one union per vertical contact between a run and a run of the row above (atomicMin hooks)
+//   3. flatten every pixel points at its component root (= smallest linear index = first pixel in raster order)
+//   4. rank    roots are numbered by a block-wide prefix sum in raster order -> scipy.ndimage.label numbering
+//   5. relabel
+// RANK == false stops after phase 3 (roots only; used by add_dropped_objects).
+template <typename T, bool RANK>
+__global__ void __launch_bounds__(1024) ccl_plane_kernel(const T* __restrict__ mask, int* __restrict__ L,
+                                                        int* __restrict__ out, int* __restrict__ count, int H, int W) {
   const long hw = (long)H * W;
-  int* Lp = L + (long)blockIdx.y * hw;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < hw; i += (long)gridDim.x * blockDim.x) {
-    if (Lp[i] < 0) continue;
-    const int x = i % W;
-    if (x > 0 && Lp[i - 1] >= 0) uf_union(Lp, (int)i, (int)i - 1);
-    if (i >= W && Lp[i - W] >= 0) uf_union(Lp, (int)i, (int)i - W);
+  const T* mp = mask + (long)blockIdx.x * hw;
+  int* Lp = L + (long)blockIdx.x * hw;
+  int* op = RANK ? out + (long)blockIdx.x * hw : nullptr;
+  // 1. runs
+  for (long i = threadIdx.x; i < hw; i += blockDim.x) {
+    const int x = (int)(i % W);
+    if (mp[i] == 0) { Lp[i] = -1; continue; }
+    if (x > 0 && mp[i - 1] != 0) continue;  // not a run start: filled in by the thread that owns the start
+    long j = i;
+    const long row_end = i - x + W;
+    while (j < row_end && mp[j] != 0) { Lp[j] = (int)i; ++j; }
   }
-}
-__global__ void ccl_flatten_kernel(int* __restrict__ L, long hw) {
-  int* Lp = L + (long)blockIdx.y * hw;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < hw; i += (long)gridDim.x * blockDim.x)
-    if (Lp[i] >= 0) Lp[i] = uf_find(Lp, (int)i);
-}
-// one block per plane: rank the roots in raster order; writes rank at the root positions of `out`, K per plane
-__global__ void ccl_rank_kernel(const int* __restrict__ L, int* __restrict__ out, int* __restrict__ count, long hw) {
-  const int* Lp = L + (long)blockIdx.x * hw;
-  int* op = out + (long)blockIdx.x * hw;
+  __syncthreads();
+  // 2. vertical contacts
+  for (long i = threadIdx.x + W; i < hw; i += blockDim.x) {
+    if (mp[i] == 0 || mp[i - W] == 0) continue;
+    const int x = (int)(i % W);
+    const bool first_contact = (x == 0) || mp[i - 1] == 0 || mp[i - W - 1] == 0;
+    if (first_contact) uf_union(Lp, Lp[i], Lp[i - W]);
+  }
+  __syncthreads();
+  // 3. flatten
+  for (long i = threadIdx.x; i < hw; i += blockDim.x)
+    if (Lp[i] >= 0) Lp[i] = uf_find(Lp, Lp[i]);
+  if (!RANK) return;
+  __syncthreads();
+  // 4. rank the roots in raster order
   const long chunk = (hw + blockDim.x - 1) / blockDim.x;
   const long b = threadIdx.x * chunk, e = min(hw, b + chunk);
   int local = 0;
@@ -143,28 +156,26 @@ __global__ void ccl_rank_kernel(const int* __restrict__ L, int* __restrict__ out
   if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
   __syncthreads();
   if (threadIdx.x < 32) {
-    int v = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0;
-    int s = v;
+    const int v = warp_sums[threadIdx.x];
+    int sc = v;
     for (int o = 1; o < 32; o <<= 1) {
-      const int n = __shfl_up_sync(0xffffffffu, s, o);
-      if (threadIdx.x >= o) s += n;
+      const int n = __shfl_up_sync(0xffffffffu, sc, o);
+      if (threadIdx.x >= o) sc += n;
     }
-    warp_sums[threadIdx.x] = s - v;  // exclusive
-    if (threadIdx.x == 31) total = s;
+    warp_sums[threadIdx.x] = sc - v;  // exclusive
+    if (threadIdx.x == 31) total = sc;
   }
   __syncthreads();
-  int run = warp_sums[threadIdx.x >> 5] + incl - local;  // exclusive prefix of this thread's chunk
+  int run = warp_sums[threadIdx.x >> 5] + incl - local;
   for (long i = b; i < e; ++i)
     if (Lp[i] == (int)i) op[i] = ++run;
   if (threadIdx.x == 0 && count != nullptr) count[blockIdx.x] = total;
-}
-__global__ void ccl_relabel_kernel(const int* __restrict__ L, int* __restrict__ out, long hw) {
-  const int* Lp = L + (long)blockIdx.y * hw;
-  int* op = out + (long)blockIdx.y * hw;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < hw; i += (long)gridDim.x * blockDim.x) {
+  __syncthreads();
+  // 5. relabel
+  for (long i = threadIdx.x; i < hw; i += blockDim.x) {
     const int r = Lp[i];
     if (r < 0) op[i] = 0;
-    else if (r != (int)i) op[i] = op[r];  // roots already hold their rank
+    else if (r != (int)i) op[i] = op[r];
   }
 }
 
@@ -240,6 +251,42 @@ __global__ void score_finalize_kernel(const double* __restrict__ sums, const int
   scores[i] = c > 0 ? (sums[i] / (double)c) * sqrt((double)c) : nan("");
 }
 
+// build_score with one CTA per plane and no host round trip: every thread walks a CONTIGUOUS pixel range and keeps a
+// running (label, sum, count); it flushes with one native fp64 global atomic only when the label changes (a few times
+// per thread, since instances are blobs), so there is no same-address atomic storm.  Scores are written at a fixed
+// stride `kcap` per plane.  counts[plane] = number of labels of the plane (from the labelling step).
+template <typename T>
+__global__ void __launch_bounds__(1024) score_plane_kernel(const int* __restrict__ labels, const T* __restrict__ prob,
+                                                          const int* __restrict__ counts, double* __restrict__ scores,
+                                                          double* __restrict__ gsum, int* __restrict__ gcnt, long hw,
+                                                          int kcap) {
+  const int plane = blockIdx.x;
+  const int K = min(counts[plane], kcap);
+  double* ps = gsum + (long)plane * kcap;
+  int* pc = gcnt + (long)plane * kcap;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) { ps[i] = 0.0; pc[i] = 0; }
+  __syncthreads();
+  const long base = (long)plane * hw;
+  const long chunk = (hw + blockDim.x - 1) / blockDim.x;
+  const long b = threadIdx.x * chunk, e = min(hw, b + chunk);
+  int cur = 0, cnt = 0;
+  double sum = 0.0;
+  for (long i = b; i < e; ++i) {
+    const int l = labels[base + i];
+    if (l != cur) {
+      if (cur > 0 && cur <= kcap) { atomicAdd(&ps[cur - 1], sum); atomicAdd(&pc[cur - 1], cnt); }
+      cur = l; cnt = 0; sum = 0.0;
+    }
+    if (l > 0) { sum += (double)prob[base + i]; ++cnt; }
+  }
+  if (cur > 0 && cur <= kcap) { atomicAdd(&ps[cur - 1], sum); atomicAdd(&pc[cur - 1], cnt); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int c = pc[i];
+    scores[(long)plane * kcap + i] = c > 0 ? (ps[i] / (double)c) * sqrt((double)c) : nan("");
+  }
+}
+
 }  // namespace mcb
 
 using namespace mcb;
@@ -278,19 +325,9 @@ extern "C" int mcb_threshold_layers(const void* prob, int prob_is_f64, const dou
 extern "C" int mcb_ccl_label(const void* mask, int mask_is_i32, int* labels, int* workspace, int* counts, int planes,
                              int h, int w, void* stream) {
   MCB_REQUIRE(mask && labels && workspace, "ccl: null pointer");
-  const long hw = (long)h * w;
-  MCB_REQUIRE(hw < (1L << 31), "ccl: plane too large");
-  dim3 grid = plane_grid(hw, planes, 256);
-  if (mask_is_i32) ccl_init_kernel<int><<<grid, 256, 0, ST>>>((const int*)mask, workspace, hw);
-  else ccl_init_kernel<uint8_t><<<grid, 256, 0, ST>>>((const uint8_t*)mask, workspace, hw);
-  MCB_LAUNCH_CHECK();
-  ccl_merge_kernel<<<grid, 256, 0, ST>>>(workspace, h, w);
-  MCB_LAUNCH_CHECK();
-  ccl_flatten_kernel<<<grid, 256, 0, ST>>>(workspace, hw);
-  MCB_LAUNCH_CHECK();
-  ccl_rank_kernel<<<planes, 1024, 0, ST>>>(workspace, labels, counts, hw);
-  MCB_LAUNCH_CHECK();
-  ccl_relabel_kernel<<<grid, 256, 0, ST>>>(workspace, labels, hw);
+  MCB_REQUIRE((long)h * w < (1L << 31), "ccl: plane too large");
+  if (mask_is_i32) ccl_plane_kernel<int, true><<<planes, 1024, 0, ST>>>((const int*)mask, workspace, labels, counts, h, w);
+  else ccl_plane_kernel<uint8_t, true><<<planes, 1024, 0, ST>>>((const uint8_t*)mask, workspace, labels, counts, h, w);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }
@@ -321,11 +358,7 @@ extern "C" int mcb_add_dropped_objects(const uint8_t* original, const uint8_t* p
   int* roots = workspace;
   int* keep = workspace + (long)planes * hw;
   dim3 grid = plane_grid(hw, planes, 256);
-  ccl_init_kernel<uint8_t><<<grid, 256, 0, ST>>>(original, roots, hw);
-  MCB_LAUNCH_CHECK();
-  ccl_merge_kernel<<<grid, 256, 0, ST>>>(roots, h, w);
-  MCB_LAUNCH_CHECK();
-  ccl_flatten_kernel<<<grid, 256, 0, ST>>>(roots, hw);
+  ccl_plane_kernel<uint8_t, false><<<planes, 1024, 0, ST>>>(original, roots, nullptr, nullptr, h, w);
   MCB_LAUNCH_CHECK();
   MCB_CHECK_CUDA(cudaMemsetAsync(keep, 0, (size_t)planes * hw * sizeof(int), ST));
   dropped_mark_kernel<<<grid, 256, 0, ST>>>(roots, processed, keep, hw);
@@ -350,6 +383,20 @@ extern "C" int mcb_instance_scores(const int* labels, const void* prob, int prob
     score_accumulate_kernel<float><<<grid, 256, 0, ST>>>(labels, (const float*)prob, offsets, sums, counts, hw);
   MCB_LAUNCH_CHECK();
   score_finalize_kernel<<<blocks_for(total_instances, 256), 256, 0, ST>>>(sums, counts, scores, total_instances);
+  MCB_LAUNCH_CHECK();
+  return MCB_OK;
+}
+
+extern "C" int mcb_instance_scores_strided(const int* labels, const void* prob, int prob_is_f64, const int* counts,
+                                           double* scores, double* gsum_ws, int* gcnt_ws, int kcap, int planes, int h,
+                                           int w, void* stream) {
+  MCB_REQUIRE(labels && prob && counts && scores && gsum_ws && gcnt_ws, "scores_strided: null pointer");
+  MCB_REQUIRE(kcap >= 1, "scores_strided: kcap %d", kcap);
+  const long hw = (long)h * w;
+  if (prob_is_f64)
+    score_plane_kernel<double><<<planes, 1024, 0, ST>>>(labels, (const double*)prob, counts, scores, gsum_ws, gcnt_ws, hw, kcap);
+  else
+    score_plane_kernel<float><<<planes, 1024, 0, ST>>>(labels, (const float*)prob, counts, scores, gsum_ws, gcnt_ws, hw, kcap);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

@@ -124,9 +124,12 @@ class Plan:
         if self.training:
             F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z), cflops, _nb(x, w16, z), desc)
         else:
-            F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, out=z), cflops, _nb(x, w16, z))
-            F.add("bn_finalize", lambda: ops.bn_eval_params(bn.gamma, bn.beta, bnmod.running_mean, bnmod.running_var,
-                                                           bn.scale, bn.shift, BN_EPS))
+            # inference: BatchNorm is a per-channel affine known up front -> folded into the conv epilogue together with
+            # the residual add and the ReLU; no pre-BN tensor is materialised (z IS the block output here)
+            do_relu = bool(relu) if relu is not None else False
+            F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, bias=bn.shift, relu=do_relu, scale=bn.scale,
+                                                   residual=residual, out=z), cflops, _nb(x, w16, z, residual), desc)
+            return z, z, bn
         if relu is None:
             return None, z, bn
         y = out if out is not None else self.act(*z.shape)
@@ -205,12 +208,12 @@ class Plan:
         bn0 = self.bn_state(enc.bn1)
         if train:
             F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, stats=bn0.stats, out=z0), sflops, _nb(col, z0))
+            a0 = self.act(*z0.shape)
+            self.bn_apply_op(z0, bn0, a0, True)
         else:
-            F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, out=z0), sflops, _nb(col, z0))
-            F.add("bn_finalize", lambda: ops.bn_eval_params(bn0.gamma, bn0.beta, enc.bn1.running_mean,
-                                                           enc.bn1.running_var, bn0.scale, bn0.shift, BN_EPS))
-        a0 = self.act(*z0.shape)
-        self.bn_apply_op(z0, bn0, a0, True)
+            F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, bias=bn0.shift, relu=True, scale=bn0.scale,
+                                                   out=z0), sflops, _nb(col, z0))
+            a0 = z0
         c1 = self.act(n, h // 4, w // 4, 64)
         F.add("maxpool", lambda: ops.maxpool2_fwd(a0, c1), 0, _nb(a0, c1))
         if train:
@@ -292,6 +295,15 @@ class Plan:
         F = self.fwd_ops
         is_bottleneck = hasattr(blk, "conv3")
         convs = [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)] + ([(blk.conv3, blk.bn3)] if is_bottleneck else [])
+        if not train:
+            cur = x
+            for conv, bnm in convs[:-1]:
+                cur, _, _ = self.conv_bn(cur, conv, bnm, True)
+            ident = x
+            if blk.downsample is not None:
+                ident, _, _ = self.conv_bn(x, blk.downsample[0], blk.downsample[1], False)
+            out, _, _ = self.conv_bn(cur, convs[-1][0], convs[-1][1], True, residual=ident)
+            return out
         acts = [x]
         units = []
         cur = x
@@ -383,7 +395,19 @@ class Plan:
         return out
 
     # ------------------------------------------------------------------------------------------ execution
+    def _bn_table(self):
+        if getattr(self, "_bn_tab", None) is None:
+            rows = [[b.gamma.data_ptr(), b.beta.data_ptr(), b.mod.running_mean.data_ptr(), b.mod.running_var.data_ptr(),
+                     b.scale.data_ptr(), b.shift.data_ptr(), b.c] for b in self._bns]
+            self._bn_tab = torch.tensor(rows, dtype=torch.int64, device=self.dev)
+            self._bn_maxc = max(b.c for b in self._bns)
+        return self._bn_tab
+
     def _run_fwd(self):
+        if not self.training:
+            from . import _lib as L
+            tab = self._bn_table()
+            L.fcall("mcb_bn_eval_params_batched", tab.data_ptr(), len(self._bns), self._bn_maxc, BN_EPS)
         if self.training:
             self._stats_arena.zero_()
         for op in self.fwd_ops:

@@ -36,7 +36,7 @@ def unpack_convt_weight(wp, k=4):
     return wp.reshape(k, k, co, ci).permute(3, 2, 0, 1).contiguous()
 
 
-def conv_fwd(x, w, ksize, stride=1, bias=None, relu=False, stats=None, x2=None, out=None):
+def conv_fwd(x, w, ksize, stride=1, bias=None, relu=False, stats=None, x2=None, out=None, scale=None, residual=None):
     _chk(x); _chk(w)
     n, h, wd, c0 = x.shape
     c1 = 0
@@ -57,6 +57,8 @@ def conv_fwd(x, w, ksize, stride=1, bias=None, relu=False, stats=None, x2=None, 
     a.relu = int(relu)
     a.stats = _chk(stats, torch.float32).data_ptr() if stats is not None else None
     a.y = _chk(out).data_ptr()
+    a.scale = _chk(scale, torch.float32).data_ptr() if scale is not None else None
+    a.residual = _chk(residual).data_ptr() if residual is not None else None
     L.call("mcb_conv_fwd", a)
     return out
 

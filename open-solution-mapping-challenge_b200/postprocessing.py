@@ -128,6 +128,20 @@ def scores_batch(labels, probs, counts):
     return scores[:total], offsets_h, counts_h
 
 
+def scores_strided(labels, probs, counts, kcap=1024):
+    """build_score without a host round trip: labels (P,H,W) int32, probs (P,H,W) f32|f64, counts (P,) int32 (labels per
+    plane) -> scores (P, kcap) float64 on the device; entries beyond counts[p] are undefined.  The caller checks
+    counts.max() <= kcap after its single device->host copy (else re-run with a larger kcap)."""
+    assert labels.is_cuda and labels.is_contiguous() and probs.is_contiguous()
+    p, h, w = labels.shape
+    scores = torch.empty((p, kcap), dtype=torch.float64, device=labels.device)
+    gsum = torch.empty((p, kcap), dtype=torch.float64, device=labels.device)
+    gcnt = torch.empty((p, kcap), dtype=torch.int32, device=labels.device)
+    L.fcall("mcb_instance_scores_strided", labels.data_ptr(), probs.data_ptr(), int(probs.dtype == torch.float64),
+            counts.data_ptr(), scores.data_ptr(), gsum.data_ptr(), gcnt.data_ptr(), int(kcap), p, h, w)
+    return scores
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # reference-signature per-image functions (numpy in / numpy out)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -281,8 +295,9 @@ class MaskPostprocessor:
         self.erode, self.dilate = erode_selem_size, dilate_selem_size
         self.category_layers = category_layers or CATEGORY_LAYERS
 
-    def run_device(self, probs):
-        """probs (N, C, S, S) float32 cuda -> (labels int32 (N,L,H,W), scores float64, offsets, counts, probs_used)"""
+    def run_device(self, probs, kcap=1024):
+        """probs (N, C, S, S) float32 cuda -> (labels int32 (N,L,H,W), scores float64 (N*L, kcap), counts int32 (N*L,),
+        probabilities used).  No host synchronisation inside."""
         assert probs.is_cuda and probs.dtype == torch.float32
         probs = probs.contiguous()
         if self.mode == "resize":
@@ -297,16 +312,21 @@ class MaskPostprocessor:
         if self.dilate > 0:
             labels = morph_batch(labels, self.dilate, dilation=True)
         n, l, h, w = labels.shape
-        p = min(l, pr.shape[1])
-        if p != l or p != pr.shape[1]:
+        if l != pr.shape[1]:
             raise NotImplementedError("score pairing needs as many layers as probability channels (CATEGORY_LAYERS=[1,1])")
-        scores, offs, cnts = scores_batch(labels.view(n * l, h, w), pr.view(n * l, h, w), counts)
-        return labels, scores, offs, cnts, pr
+        scores = scores_strided(labels.view(n * l, h, w), pr.view(n * l, h, w), counts, kcap)
+        return labels, scores, counts, pr
 
     def transform(self, images, **_):
         probs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.stack(images)))
         probs = probs.to(device=_dev(), dtype=torch.float32)
-        labels, scores, offs, cnts, _pr = self.run_device(probs)
+        kcap = 1024
+        while True:
+            labels, scores, counts, _pr = self.run_device(probs, kcap)
+            cnt = counts.cpu().numpy()
+            if cnt.size == 0 or int(cnt.max()) <= kcap:
+                break
+            kcap = int(cnt.max())
         lab = labels.cpu().numpy()
         s = scores.cpu().numpy()
         n, l = lab.shape[:2]
@@ -314,8 +334,7 @@ class MaskPostprocessor:
         for i in range(n):
             sc = []
             for j in range(l):
-                pidx = i * l + j
-                vals = s[offs[pidx]:offs[pidx] + cnts[pidx]]
+                vals = s[i * l + j, :cnt[i * l + j]]
                 sc.append([np.ma.masked if np.isnan(v) else v for v in vals])
             out.append((lab[i], sc))
         return {"y_pred": out}

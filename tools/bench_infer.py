@@ -1,0 +1,65 @@
+"""BASELINE.json configs[3]: inference-only ResNet101-UNet + full post-processing, batch 64, 300x300 tiles, 1 GPU.
+Reports the forward time, the post-processing time (threshold -> [CRF] -> erode -> label -> dilate -> score
+[-> watershed]) and post-processing as a share of the step.  Everything stays on the device; the only D2H transfers
+are the per-plane instance counts (256 B) inside the score step and the final labels/scores."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import bench
+import mcb200
+from mcb200 import ops, postprocessing as G
+from mcb200.models import PyTorchUNet
+from oracle import synthetic
+
+enc = int(os.environ.get("ENC", "101")); b = int(os.environ.get("BATCH", "64")); s = int(os.environ.get("SIZE", "320"))
+dev = torch.device("cuda:0")
+torch.manual_seed(1234)
+m = PyTorchUNet(**bench.unet_config("ResNet%d" % enc)); m._to_device()
+net = m.model; net.eval()
+x, _ = synthetic.train_batch(b, s, seed=1234)
+X = torch.from_numpy(x).to(dev)
+# realistic probability maps for the post-processing (a random-init net predicts noise): synthetic buildings
+probs_syn = torch.from_numpy(synthetic.probability_maps(b, s, seed=7)).to(dev)
+mode = "crop" if s == 320 else "resize"
+pp = G.MaskPostprocessor((300, 300), mode, erode_selem_size=2, dilate_selem_size=2)
+
+
+def ev(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+with torch.no_grad():
+    t_fwd = ev(lambda: ops.softmax2(net(X)))
+t_pp = ev(lambda: pp.run_device(probs_syn))
+crop = probs_syn[:, :, 10:310, 10:310].contiguous() if s == 320 else G.resize_batch(probs_syn, (300, 300)).float()
+img = X[:, :, 10:310, 10:310].contiguous() if s == 320 else torch.randn(b, 3, 300, 300, device=dev)
+t_crf = ev(lambda: G.dense_crf_batch(img, crop), n=3, warm=1)
+p1 = crop[:, 1].contiguous()
+t_ws = ev(lambda: G.watershed_split(p1, hi=0.8, lo=0.5), n=3, warm=1)
+stages = {}
+pr = crop
+stages["threshold"] = ev(lambda: G.threshold_batch(pr))
+masks = G.threshold_batch(pr)
+stages["erode+add_dropped(2)"] = ev(lambda: G.erode_batch(masks, 2))
+stages["label"] = ev(lambda: G.label_batch(masks))
+lab, cnt = G.label_batch(masks, return_counts=True)
+stages["dilate(2)"] = ev(lambda: G.morph_batch(lab, 2, True))
+stages["score"] = ev(lambda: G.scores_batch(lab.view(-1, 300, 300), pr.reshape(-1, 300, 300), cnt))
+if mode == "resize":
+    stages["resize"] = ev(lambda: G.resize_batch(probs_syn, (300, 300)))
+out = {"workload": "UNetResNet-%d eval forward + softmax, batch %d @%dx%d, then mask post-processing to 300x300 (%s)" % (enc, b, s, s, mode),
+       "forward_ms": round(t_fwd, 3), "postproc_ms": round(t_pp, 3), "postproc_share_of_step": round(t_pp / (t_fwd + t_pp), 4),
+       "tiles_per_s_inference_plus_postproc": round(b / ((t_fwd + t_pp) * 1e-3), 1),
+       "dense_crf_5iter_ms": round(t_crf, 3), "watershed_ms": round(t_ws, 3),
+       "stages_ms": {k: round(v, 3) for k, v in stages.items()},
+       "postproc_algorithmic_MB": round(b * 1.44, 1), "postproc_GBps_vs_1.44MB_per_image": round(b * 1.44e-3 / (t_pp * 1e-3), 1)}
+print(json.dumps(out))
