@@ -104,13 +104,62 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     a = old;
   }
 }
-// One CTA (1024 threads) per plane runs the whole labelling; the phases are separated by __syncthreads():
-//   1. rows    every horizontal run gets the linear index of its first pixel (no atomics)
-//   2. merge   one union per vertical contact between a run and a run of the row above (atomicMin hooks)
-//   3. flatten every pixel points at its component root (= smallest linear index = first pixel in raster order)
-//   4. rank    roots are numbered by a block-wide prefix sum in raster order -> scipy.ndimage.label numbering
-//   5. relabel
-// RANK == false stops after phase 3 (roots only; used by add_dropped_objects).
+// Two launches.
+//  (1) ccl_strip_kernel: a CTA labels one strip of 32 rows entirely in SHARED memory — horizontal runs get the index of
+//      their first pixel (no atomics), one union per vertical contact between runs (shared-memory atomicMin hooks),
+//      flatten — and writes strip-local roots as global pixel indices.
+//  (2) ccl_plane_kernel: one CTA per plane stitches the strips (unions along the 32-row borders), flattens, ranks the
+//      roots in raster order with a block-wide prefix sum (-> scipy.ndimage.label numbering) and relabels.
+// RANK == false stops after the flatten (roots only; used by add_dropped_objects).
+constexpr int CCL_STRIP = 32;
+
+__device__ __forceinline__ int uf_find_s(const int* L, int a) {
+  int p = L[a];
+  while (p != a) { a = p; p = L[a]; }
+  return a;
+}
+__device__ __forceinline__ void uf_union_s(int* L, int a, int b) {
+  while (true) {
+    a = uf_find_s(L, a);
+    b = uf_find_s(L, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) ccl_strip_kernel(const T* __restrict__ mask, int* __restrict__ L, int H, int W) {
+  extern __shared__ int s_ccl[];
+  const int y0 = blockIdx.x * CCL_STRIP;
+  const int rows = min(CCL_STRIP, H - y0);
+  const int n = rows * W;
+  int* sl = s_ccl;                                              // [n] local parent (local linear index) or -1
+  uint8_t* sm = reinterpret_cast<uint8_t*>(s_ccl + CCL_STRIP * W);  // [n] mask
+  const long base = (long)blockIdx.y * H * W + (long)y0 * W;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = mask[base + i] != 0 ? 1 : 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = i % W;
+    if (!sm[i]) { sl[i] = -1; continue; }
+    if (x > 0 && sm[i - 1]) continue;
+    const int row_end = i - x + W;
+    for (int j = i; j < row_end && sm[j]; ++j) sl[j] = i;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x + W; i < n; i += blockDim.x) {
+    if (!sm[i] || !sm[i - W]) continue;
+    const int x = i % W;
+    if (x == 0 || !sm[i - 1] || !sm[i - W - 1]) uf_union_s(sl, sl[i], sl[i - W]);
+  }
+  __syncthreads();
+  const int goff = y0 * W;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    L[base + i] = sm[i] ? goff + uf_find_s(sl, sl[i]) : -1;
+}
+
 template <typename T, bool RANK>
 __global__ void __launch_bounds__(1024) ccl_plane_kernel(const T* __restrict__ mask, int* __restrict__ L,
                                                         int* __restrict__ out, int* __restrict__ count, int H, int W) {
@@ -118,30 +167,20 @@ __global__ void __launch_bounds__(1024) ccl_plane_kernel(const T* __restrict__ m
   const T* mp = mask + (long)blockIdx.x * hw;
   int* Lp = L + (long)blockIdx.x * hw;
   int* op = RANK ? out + (long)blockIdx.x * hw : nullptr;
-  // 1. runs
-  for (long i = threadIdx.x; i < hw; i += blockDim.x) {
-    const int x = (int)(i % W);
-    if (mp[i] == 0) { Lp[i] = -1; continue; }
-    if (x > 0 && mp[i - 1] != 0) continue;  // not a run start: filled in by the thread that owns the start
-    long j = i;
-    const long row_end = i - x + W;
-    while (j < row_end && mp[j] != 0) { Lp[j] = (int)i; ++j; }
-  }
-  __syncthreads();
-  // 2. vertical contacts
-  for (long i = threadIdx.x + W; i < hw; i += blockDim.x) {
+  // stitch the strips: one union per vertical contact across each 32-row border
+  const int borders = (H - 1) / CCL_STRIP;
+  for (int k = threadIdx.x; k < borders * W; k += blockDim.x) {
+    const int x = k % W;
+    const long i = (long)(k / W + 1) * CCL_STRIP * W + x;
     if (mp[i] == 0 || mp[i - W] == 0) continue;
-    const int x = (int)(i % W);
-    const bool first_contact = (x == 0) || mp[i - 1] == 0 || mp[i - W - 1] == 0;
-    if (first_contact) uf_union(Lp, Lp[i], Lp[i - W]);
+    if (x == 0 || mp[i - 1] == 0 || mp[i - W - 1] == 0) uf_union(Lp, Lp[i], Lp[i - W]);
   }
   __syncthreads();
-  // 3. flatten
   for (long i = threadIdx.x; i < hw; i += blockDim.x)
     if (Lp[i] >= 0) Lp[i] = uf_find(Lp, Lp[i]);
   if (!RANK) return;
   __syncthreads();
-  // 4. rank the roots in raster order
+  // rank the roots in raster order
   const long chunk = (hw + blockDim.x - 1) / blockDim.x;
   const long b = threadIdx.x * chunk, e = min(hw, b + chunk);
   int local = 0;
@@ -171,12 +210,29 @@ __global__ void __launch_bounds__(1024) ccl_plane_kernel(const T* __restrict__ m
     if (Lp[i] == (int)i) op[i] = ++run;
   if (threadIdx.x == 0 && count != nullptr) count[blockIdx.x] = total;
   __syncthreads();
-  // 5. relabel
   for (long i = threadIdx.x; i < hw; i += blockDim.x) {
     const int r = Lp[i];
     if (r < 0) op[i] = 0;
     else if (r != (int)i) op[i] = op[r];
   }
+}
+
+template <typename T, bool RANK>
+static int launch_ccl(const T* mask, int* workspace, int* labels, int* counts, int planes, int h, int w,
+                      cudaStream_t st) {
+  const size_t smem = (size_t)CCL_STRIP * w * 5;
+  if (smem > 200 * 1024) return fail(MCB_ERR_UNSUPPORTED, "ccl: width %d too large for the strip kernel", w);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    MCB_CHECK_CUDA(cudaFuncSetAttribute(ccl_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((h + CCL_STRIP - 1) / CCL_STRIP, planes);
+  ccl_strip_kernel<T><<<grid, 512, smem, st>>>(mask, workspace, h, w);
+  MCB_LAUNCH_CHECK();
+  ccl_plane_kernel<T, RANK><<<planes, 1024, 0, st>>>(mask, workspace, labels, counts, h, w);
+  MCB_LAUNCH_CHECK();
+  return MCB_OK;
 }
 
 // ------------------------------------------------------------------------------------------ morphology (P3, P5)
@@ -282,8 +338,9 @@ __global__ void __launch_bounds__(1024) score_plane_kernel(const int* __restrict
   if (cur > 0 && cur <= kcap) { atomicAdd(&ps[cur - 1], sum); atomicAdd(&pc[cur - 1], cnt); }
   __syncthreads();
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    const int c = pc[i];
-    scores[(long)plane * kcap + i] = c > 0 ? (ps[i] / (double)c) * sqrt((double)c) : nan("");
+    const int c = __ldcg(&pc[i]);  // the atomics landed in L2: read around L1
+    const double sm = __ldcg(&ps[i]);
+    scores[(long)plane * kcap + i] = c > 0 ? (sm / (double)c) * sqrt((double)c) : nan("");
   }
 }
 
@@ -326,10 +383,8 @@ extern "C" int mcb_ccl_label(const void* mask, int mask_is_i32, int* labels, int
                              int h, int w, void* stream) {
   MCB_REQUIRE(mask && labels && workspace, "ccl: null pointer");
   MCB_REQUIRE((long)h * w < (1L << 31), "ccl: plane too large");
-  if (mask_is_i32) ccl_plane_kernel<int, true><<<planes, 1024, 0, ST>>>((const int*)mask, workspace, labels, counts, h, w);
-  else ccl_plane_kernel<uint8_t, true><<<planes, 1024, 0, ST>>>((const uint8_t*)mask, workspace, labels, counts, h, w);
-  MCB_LAUNCH_CHECK();
-  return MCB_OK;
+  if (mask_is_i32) return launch_ccl<int, true>((const int*)mask, workspace, labels, counts, planes, h, w, ST);
+  return launch_ccl<uint8_t, true>((const uint8_t*)mask, workspace, labels, counts, planes, h, w, ST);
 }
 
 extern "C" int mcb_morph_rect(const void* in, void* out, int is_i32, int is_dilation, int size, int planes, int h,
@@ -358,8 +413,7 @@ extern "C" int mcb_add_dropped_objects(const uint8_t* original, const uint8_t* p
   int* roots = workspace;
   int* keep = workspace + (long)planes * hw;
   dim3 grid = plane_grid(hw, planes, 256);
-  ccl_plane_kernel<uint8_t, false><<<planes, 1024, 0, ST>>>(original, roots, nullptr, nullptr, h, w);
-  MCB_LAUNCH_CHECK();
+  if (int r = launch_ccl<uint8_t, false>(original, roots, nullptr, nullptr, planes, h, w, ST)) return r;
   MCB_CHECK_CUDA(cudaMemsetAsync(keep, 0, (size_t)planes * hw * sizeof(int), ST));
   dropped_mark_kernel<<<grid, 256, 0, ST>>>(roots, processed, keep, hw);
   MCB_LAUNCH_CHECK();

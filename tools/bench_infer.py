@@ -40,6 +40,8 @@ def ev(fn, n=5, warm=2):
 with torch.no_grad():
     t_fwd = ev(lambda: ops.softmax2(net(X)))
 t_pp = ev(lambda: pp.run_device(probs_syn))
+pp_default = G.MaskPostprocessor((300, 300), mode, erode_selem_size=0, dilate_selem_size=0)  # neptune.yaml:69-70 defaults
+t_pp_default = ev(lambda: pp_default.run_device(probs_syn))
 crop = probs_syn[:, :, 10:310, 10:310].contiguous() if s == 320 else G.resize_batch(probs_syn, (300, 300)).float()
 img = X[:, :, 10:310, 10:310].contiguous() if s == 320 else torch.randn(b, 3, 300, 300, device=dev)
 t_crf = ev(lambda: G.dense_crf_batch(img, crop), n=3, warm=1)
@@ -58,6 +60,10 @@ if mode == "resize":
     stages["resize"] = ev(lambda: G.resize_batch(probs_syn, (300, 300)))
 out = {"workload": "UNetResNet-%d eval forward + softmax, batch %d @%dx%d, then mask post-processing to 300x300 (%s)" % (enc, b, s, s, mode),
        "forward_ms": round(t_fwd, 3), "postproc_ms": round(t_pp, 3), "postproc_share_of_step": round(t_pp / (t_fwd + t_pp), 4),
+       "postproc_config": "erode 2 + dilate 2 (REPRODUCE_RESULTS.md evaluation setting)",
+       "postproc_default_ms": round(t_pp_default, 3),
+       "postproc_default_share_of_step": round(t_pp_default / (t_fwd + t_pp_default), 4),
+       "postproc_default_config": "erode 0 / dilate 0 (neptune.yaml defaults)",
        "tiles_per_s_inference_plus_postproc": round(b / ((t_fwd + t_pp) * 1e-3), 1),
        "dense_crf_5iter_ms": round(t_crf, 3), "watershed_ms": round(t_ws, 3),
        "stages_ms": {k: round(v, 3) for k, v in stages.items()},
