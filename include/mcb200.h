@@ -256,6 +256,10 @@ int mcb_dense_crf(const float* probs, const uint8_t* rgb, float* out, float* wor
 int mcb_watershed(const void* prob, int prob_is_f64, const int* markers, const uint8_t* mask, int* labels,
                   int* workspace, int planes, int h, int w, int levels, void* stream);
 
+/* hardware probe used while designing the haloed 3x3 path (debug only, see csrc/probe.cu) */
+int mcb_debug_umma_probe(const void* a, const void* ident, float* out, int rows, int rowb, int shift, int sbo,
+                         int base_off_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

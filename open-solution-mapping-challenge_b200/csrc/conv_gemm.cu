@@ -40,46 +40,59 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int BN, int BK, bool B_MN>
+template <int BN, int BK, bool B_MN, bool HALO>
 static int launch_conv_inst(const ConvGemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MCB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024));
+    MCB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BK, B_MN, HALO>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, BK, B_MN><<<grid, kConvThreads, smem, st>>>(p);
+  conv_gemm_kernel<BN, BK, B_MN, HALO><<<grid, kConvThreads, smem, st>>>(p);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }
 
-template <int BK, bool B_MN>
+template <int BK, bool B_MN, bool HALO>
 static int launch_conv_bn(int BN, const ConvGemmParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   switch (BN) {
-    case 256: return launch_conv_inst<256, BK, B_MN>(p, grid, smem, st);
-    case 128: return launch_conv_inst<128, BK, B_MN>(p, grid, smem, st);
-    case 64: return launch_conv_inst<64, BK, B_MN>(p, grid, smem, st);
-    case 32: return launch_conv_inst<32, BK, B_MN>(p, grid, smem, st);
+    case 256: return launch_conv_inst<256, BK, B_MN, HALO>(p, grid, smem, st);
+    case 128: return launch_conv_inst<128, BK, B_MN, HALO>(p, grid, smem, st);
+    case 64: return launch_conv_inst<64, BK, B_MN, HALO>(p, grid, smem, st);
+    case 32: return launch_conv_inst<32, BK, B_MN, HALO>(p, grid, smem, st);
   }
   return fail(MCB_ERR_UNSUPPORTED, "unsupported BN %d", BN);
 }
 
 static int launch_conv(int BN, int BK, bool b_mn, ConvGemmParams& p, int m_tiles, int n_tiles, int phases,
-                       cudaStream_t st) {
-  const int a_bytes = 128 * BK * 2, b_bytes = BN * BK * 2;
-  const int stage = a_bytes + b_bytes;
-  const int out_bytes = 128 * BN * 2;
-  const int stat_bytes = 16 * 1024;  // (2048 / BN row groups) x BN columns x {sum, sumsq} floats == 16 KB for every BN
-  const int fixed = out_bytes + stat_bytes + 1024 /*align*/ + 1536 /*barriers, row tables*/;
+                       cudaStream_t st, bool halo = false) {
+  const int a_bytes = halo ? ((kHaloW * kHaloH * BK * 2 + 1023) / 1024) * 1024 : 128 * BK * 2;
+  const int b_bytes = BN * BK * 2;
+  const int stage = halo ? b_bytes : a_bytes + b_bytes;
+  const int out_bufs = BN <= 64 ? 4 : (BN == 128 ? 2 : 1);
+  const int out_bytes = out_bufs * 128 * BN * 2;
+  const int stat_bytes = 16 * 1024;  // two halves x 8 KB reduction scratch
+  const int fixed = out_bytes + stat_bytes + 1024 /*align*/ + 1536 /*barriers, row tables*/ + (halo ? 2 * a_bytes : 0);
   const int budget = std::min(env_int("MCB_SMEM_BUDGET_KB", 227) * 1024, 232448);
-  int stages = std::max(2, std::min(env_int("MCB_MAX_STAGES", 6), (budget - fixed) / stage));
+  int stages = std::max(2, std::min(env_int("MCB_MAX_STAGES", halo ? 9 : 6), (budget - fixed) / stage));
   p.stages = stages;
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.phases = phases;
   const size_t smem = (size_t)stages * stage + fixed;
   const long total = (long)m_tiles * n_tiles * phases;
   dim3 grid((unsigned)std::min<long>(total, num_sms()), 1, 1);
-  if (BK == 64) return b_mn ? launch_conv_bn<64, true>(BN, p, grid, smem, st) : launch_conv_bn<64, false>(BN, p, grid, smem, st);
-  return b_mn ? launch_conv_bn<32, true>(BN, p, grid, smem, st) : launch_conv_bn<32, false>(BN, p, grid, smem, st);
+  if (halo) {
+    if (BK == 64) return b_mn ? launch_conv_bn<64, true, true>(BN, p, grid, smem, st) : launch_conv_bn<64, false, true>(BN, p, grid, smem, st);
+    return b_mn ? launch_conv_bn<32, true, true>(BN, p, grid, smem, st) : launch_conv_bn<32, false, true>(BN, p, grid, smem, st);
+  }
+  if (BK == 64) return b_mn ? launch_conv_bn<64, true, false>(BN, p, grid, smem, st) : launch_conv_bn<64, false, false>(BN, p, grid, smem, st);
+  return b_mn ? launch_conv_bn<32, true, false>(BN, p, grid, smem, st) : launch_conv_bn<32, false, false>(BN, p, grid, smem, st);
+}
+
+// haloed 3x3 path: worth it when 8x16 single-image tiles cover the image without much waste
+static bool use_halo(int ksize, int stride, int W, int H) {
+  if (ksize != 3 || stride != 1 || env_int("MCB_HALO", 0) == 0) return false;
+  const double eff = (double)W * H / ((double)((W + 7) / 8) * 8 * ((H + 15) / 16) * 16);
+  return eff >= 0.8;
 }
 
 static int pick_bn(int n_total, long m_tiles, int phases) {
@@ -165,7 +178,9 @@ extern "C" int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream) {
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  pick_tile(Wo, Ho, N, 128, 1, &p.bw, &p.bh, &p.bn);
+  const bool halo = use_halo(a->ksize, a->stride, Wo, Ho);
+  if (halo) { p.bw = 8; p.bh = 16; p.bn = 1; }
+  else pick_tile(Wo, Ho, N, 128, 1, &p.bw, &p.bh, &p.bn);
   p.rows = p.bw * p.bh * p.bn;
   p.Wv = Wo; p.Hv = Ho; p.Nimg = N;
   p.tiles_x = (Wo + p.bw - 1) / p.bw;
@@ -177,8 +192,8 @@ extern "C" int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream) {
   int nt = 0;
   if (a->stride == 1) {
     for (int s = 0; s < nsrc; ++s)
-      if (int r = encode_nhwc_view(&p.tmA[s], a->x[s], N, H, W, a->cin[s], 0, a->cin[s], -1, -1, BK, p.bw, p.bh,
-                                   p.bn, swz)) return r;
+      if (int r = encode_nhwc_view(&p.tmA[s], a->x[s], N, H, W, a->cin[s], 0, a->cin[s], -1, -1, BK,
+                                   halo ? kHaloW : p.bw, halo ? kHaloH : p.bh, p.bn, swz)) return r;
     for (int ky = 0; ky < a->ksize; ++ky)
       for (int kx = 0; kx < a->ksize; ++kx)
         for (int s = 0; s < nsrc; ++s) {
@@ -213,7 +228,7 @@ extern "C" int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream) {
     p.residual = static_cast<const __nv_bfloat16*>(a->residual);
     p.mask_H = Ho; p.mask_W = Wo; p.mask_C = a->cout; p.mask_s = 1;
   }
-  return launch_conv(BN, BK, false, p, (int)m_tiles, a->cout / BN, 1, st);
+  return launch_conv(BN, BK, false, p, (int)m_tiles, a->cout / BN, 1, st, halo);
 }
 
 // =====================================================================================================
@@ -233,7 +248,9 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   const int Wv = (a->stride == 1) ? W : W / 2, Hv = (a->stride == 1) ? H : H / 2;
-  pick_tile(Wv, Hv, N, 128, 1, &p.bw, &p.bh, &p.bn);
+  const bool halo = use_halo(a->ksize, a->stride, Wv, Hv);
+  if (halo) { p.bw = 8; p.bh = 16; p.bn = 1; }
+  else pick_tile(Wv, Hv, N, 128, 1, &p.bw, &p.bh, &p.bn);
   p.rows = p.bw * p.bh * p.bn;
   p.Wv = Wv; p.Hv = Hv; p.Nimg = N;
   p.tiles_x = (Wv + p.bw - 1) / p.bw;
@@ -241,8 +258,8 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
   const long m_tiles = (long)p.tiles_x * p.tiles_y * ((N + p.bn - 1) / p.bn);
   int phases = 1;
   int nt = 0;
-  if (int r = encode_nhwc_view(&p.tmA[0], a->dy, N, Ho, Wo, a->cout, 0, a->cout, -1, -1, BK, p.bw, p.bh, p.bn,
-                               BK * 2)) return r;
+  if (int r = encode_nhwc_view(&p.tmA[0], a->dy, N, Ho, Wo, a->cout, 0, a->cout, -1, -1, BK, halo ? kHaloW : p.bw,
+                               halo ? kHaloH : p.bh, p.bn, BK * 2)) return r;
   int phase_map[4] = {0, 0, 0, 0};  // launch phase -> (py*2+px)
   if (a->stride == 1) {
     for (int ky = 0; ky < a->ksize; ++ky)
@@ -306,7 +323,7 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
     p.bn_z = static_cast<const __nv_bfloat16*>(a->bn_z);
     p.bn_mean = a->bn_mean; p.bn_invstd = a->bn_invstd; p.bn_dbeta = a->bn_dbeta; p.bn_dgamma = a->bn_dgamma;
   }
-  return launch_conv(BN, BK, true, p, (int)m_tiles, a->cin / BN, phases, st);
+  return launch_conv(BN, BK, true, p, (int)m_tiles, a->cin / BN, phases, st, halo);
 }
 
 // =====================================================================================================

@@ -93,14 +93,22 @@ __device__ __forceinline__ uint8_t* align_up_1024(uint8_t* p) {
 // TMEM accumulators (2 x BN columns) let the 8 epilogue warps drain tile i while the MMA warp is already on tile i+1.
 constexpr int kConvThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
 
-template <int BN, int BK, bool B_MN>
+// HALO (3x3, stride 1): the pixel tile is 8 wide x 16 tall in one image and ONE haloed TMA box (BK channels, 10, 18, 1)
+// per channel chunk serves all nine taps: tap (dy, dx) is the same shared-memory tile read through a descriptor whose
+// start is shifted by ((1+dy)*10 + (1+dx)) rows and whose 8-row groups are 10 rows apart (the UMMA swizzle is a function
+// of the absolute shared-memory address, so unaligned starts and a non-atom SBO are legal — csrc/probe.cu,
+// tools/probe_umma.py).  A and B then travel in separate mbarrier rings: 1 A load + 9 B loads per channel chunk.
+constexpr int kHaloW = 10, kHaloH = 18;  // (8 + 2) x (16 + 2)
+
+template <int BN, int BK, bool B_MN, bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(BK == 64 || BK == 32, "BK");
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
   constexpr int A_ROW_BYTES = BK * 2;              // 128 (SW128) or 64 (SW64)
-  constexpr int A_BYTES = 128 * A_ROW_BYTES;
+  constexpr int A_BYTES = HALO ? ((kHaloW * kHaloH * A_ROW_BYTES + 1023) / 1024) * 1024 : 128 * A_ROW_BYTES;
   constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = HALO ? B_BYTES : A_BYTES + B_BYTES;  // HALO: the ring holds B tiles; A has its own 2 slots
+  constexpr int A_RING_BYTES = HALO ? 2 * A_BYTES : 0;
   constexpr uint32_t A_LAYOUT = (BK == 64) ? tc::LAYOUT_SW128 : tc::LAYOUT_SW64;
   // MN-major B: rows are K (BK of them), each row holds min(BN,64) n-values
   constexpr int BMN_CW = (BN >= 64) ? 64 : 32;          // n-values per sub-tile row
@@ -114,23 +122,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   constexpr int OUT_ROW_BYTES = OUT_CW * 2;
   constexpr int OUT_CHUNK_BYTES = 128 * OUT_ROW_BYTES;
   constexpr int OUT_CHUNKS = BN / OUT_CW;
-  constexpr int OUT_BYTES = OUT_CHUNKS * OUT_CHUNK_BYTES;
+  // small tiles finish faster than a TMA store drains: rotate several staging buffers so the epilogue of tile i+1 never
+  // waits for the store of tile i
+  constexpr int OUT_BUFS = (BN <= 64) ? 4 : (BN == 128 ? 2 : 1);
+  constexpr int OUT_BYTES = OUT_BUFS * OUT_CHUNKS * OUT_CHUNK_BYTES;
   // statistics scratch: RG row groups x BN columns x {sum, sumsq}
   constexpr int STAT_BYTES = 2 * 8192;  // per half: (128 / (OUT_CW/8)) row groups x OUT_CW columns x {a, b} floats
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_up_1024(smem_raw);
   const int stages = p.stages;
-  uint8_t* out_stage = smem + (size_t)stages * STAGE_BYTES;            // 1024-aligned (STAGE_BYTES is)
+  uint8_t* a_ring = smem + (size_t)stages * STAGE_BYTES;               // HALO only: 2 haloed A tiles
+  uint8_t* out_stage = a_ring + A_RING_BYTES;                          // 1024-aligned (all pieces are)
   float* stat_scratch = reinterpret_cast<float*>(out_stage + OUT_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + OUT_BYTES + STAT_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* a_full_bar = tmem_empty_bar + 2;      // [2] (HALO)
+  uint64_t* a_empty_bar = a_full_bar + 2;         // [2] (HALO)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 2);
   int* row_pix = reinterpret_cast<int*>(tmem_slot + 2);  // [2][128] pixel index in the full-resolution tensor, -1 = invalid
 
-  const int warp = threadIdx.x >> 5;
+  // the shuffle makes the warp index provably warp-uniform, so the role loops below compile onto the uniform datapath
+  // (descriptors, barrier addresses and loop counters in uniform registers; no ELECT/R2UR round trip per tcgen05.mma)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int tiles_per_phase = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_per_phase * p.phases;
@@ -144,6 +160,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tc::mbar_init(&tmem_full_bar[1], 1);
     tc::mbar_init(&tmem_empty_bar[0], 8);  // one arrival per epilogue warp
     tc::mbar_init(&tmem_empty_bar[1], 8);
+    tc::mbar_init(&a_full_bar[0], 1);
+    tc::mbar_init(&a_full_bar[1], 1);
+    tc::mbar_init(&a_empty_bar[0], 1);
+    tc::mbar_init(&a_empty_bar[1], 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&p.tmB);
     tc::prefetch_tmap(&p.tmA[0]);
@@ -155,13 +175,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp walks the loop, one elected lane issues)
+    {
       const uint32_t a_bytes = (uint32_t)p.rows * A_ROW_BYTES;
       uint32_t kb = 0;
+      uint32_t ag = 0;  // HALO: haloed A tiles issued so far
+      int ring_s = 0;            // pipeline slot / phase parity, advanced without integer division: the single-thread
+      uint32_t ring_ph = 0;      // producer and MMA loops are latency chains, every instruction in them is exposed
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         // tile order: phase fastest (the phases of one pixel tile share the A tile in L2), then pixel tile, N tile
         // slowest (CTAs running together share the weight tile; a CTA keeps its N tile for many tiles in a row)
@@ -172,24 +195,62 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
         const int ncol0 = nt * BN;
         const int tap_begin = p.tap_start[phase_id], tap_end = tap_begin + p.tap_count[phase_id];
+        if (HALO) {
+          // taps are listed tap-major, source-minor: entry (t, s) at tap_begin + t * nsrc + s
+          const int nsrc = (tap_end - tap_begin) / 9;
+          for (int sidx = 0; sidx < nsrc; ++sidx) {
+            const TapDesc t0 = p.taps[tap_begin + sidx];
+            for (int ch = 0; ch < t0.nchunks; ++ch, ++ag) {
+              const int as = ag & 1;
+              tc::mbar_wait(&a_empty_bar[as], ((ag >> 1) & 1) ^ 1);
+              if (tc::elect_one()) {
+                tc::mbar_expect_tx(&a_full_bar[as], (uint32_t)(kHaloW * kHaloH * A_ROW_BYTES));
+                tc::tma_load_4d(a_ring + (size_t)as * A_BYTES, &p.tmA[t0.src], &a_full_bar[as], ch * BK, x0 - 1, y0 - 1, n0);
+              }
+              for (int t = 0; t < 9; ++t, ++kb) {
+                const TapDesc tap = p.taps[tap_begin + t * nsrc + sidx];
+                const int s = ring_s;
+                const uint32_t ph = ring_ph;
+                if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sb = smem + (size_t)s * STAGE_BYTES;
+                if (tc::elect_one()) {
+                  tc::mbar_expect_tx(&full_bar[s], B_BYTES);
+                  if (!B_MN) {
+                    tc::tma_load_3d(sb, &p.tmB, &full_bar[s], tap.wk0 + ch * BK, p.n_off + ncol0, tap.wtap);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < BMN_SUBS; ++j)
+                      tc::tma_load_3d(sb + j * BMN_SUB_BYTES, &p.tmB, &full_bar[s], p.n_off + ncol0 + j * BMN_CW,
+                                      tap.wk0 + ch * BK, tap.wtap);
+                  }
+                }
+              }
+            }
+          }
+          continue;
+        }
         for (int tp = tap_begin; tp < tap_end; ++tp) {
           const TapDesc tap = p.taps[tp];
           const CUtensorMap* mA = &p.tmA[tap.src];
           for (int ch = 0; ch < tap.nchunks; ++ch, ++kb) {
-            const int s = kb % stages;
-            const uint32_t ph = (kb / stages) & 1;
+            const int s = ring_s;
+            const uint32_t ph = ring_ph;
+            if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
             tc::mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
-            tc::mbar_expect_tx(&full_bar[s], a_bytes + B_BYTES);
-            tc::tma_load_4d(sa, mA, &full_bar[s], ch * BK, x0 + tap.dx, y0 + tap.dy, n0);
-            if (!B_MN) {
-              tc::tma_load_3d(sb, &p.tmB, &full_bar[s], tap.wk0 + ch * BK, p.n_off + ncol0, tap.wtap);
-            } else {
+            if (tc::elect_one()) {
+              tc::mbar_expect_tx(&full_bar[s], a_bytes + B_BYTES);
+              tc::tma_load_4d(sa, mA, &full_bar[s], ch * BK, x0 + tap.dx, y0 + tap.dy, n0);
+              if (!B_MN) {
+                tc::tma_load_3d(sb, &p.tmB, &full_bar[s], tap.wk0 + ch * BK, p.n_off + ncol0, tap.wtap);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BMN_SUBS; ++j)
-                tc::tma_load_3d(sb + j * BMN_SUB_BYTES, &p.tmB, &full_bar[s], p.n_off + ncol0 + j * BMN_CW,
-                                tap.wk0 + ch * BK, tap.wtap);
+                for (int j = 0; j < BMN_SUBS; ++j)
+                  tc::tma_load_3d(sb + j * BMN_SUB_BYTES, &p.tmB, &full_bar[s], p.n_off + ncol0 + j * BMN_CW,
+                                  tap.wk0 + ch * BK, tap.wtap);
+              }
             }
           }
         }
@@ -198,6 +259,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     uint32_t kb = 0;
+    uint32_t ag = 0;
+    int ring_s = 0;
+    uint32_t ring_ph = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int phase_id = t % p.phases;
@@ -208,12 +272,52 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       tc::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       tc::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      if (HALO) {
+        const int nsrc = (tap_end - tap_begin) / 9;
+        int i = 0;
+        for (int sidx = 0; sidx < nsrc; ++sidx) {
+          const int nch = p.taps[tap_begin + sidx].nchunks;
+          for (int ch = 0; ch < nch; ++ch, ++ag) {
+            const int as = ag & 1;
+            tc::mbar_wait(&a_full_bar[as], (ag >> 1) & 1);
+            const uint32_t a_base = tc::smem_u32(a_ring + (size_t)as * A_BYTES);
+            for (int t = 0; t < 9; ++t, ++kb, ++i) {
+              const TapDesc tap = p.taps[tap_begin + t * nsrc + sidx];
+              const int s = ring_s;
+              const uint32_t ph = ring_ph;
+              if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
+              tc::mbar_wait(&full_bar[s], ph);
+              tc::tc_fence_after();
+              if (tc::elect_one()) {
+                const uint32_t sa = a_base + (uint32_t)(((1 + tap.dy) * kHaloW + (1 + tap.dx)) * A_ROW_BYTES);
+                const uint32_t sb = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint64_t da0 = tc::make_smem_desc(sa, 16, kHaloW * A_ROW_BYTES, A_LAYOUT);
+                uint64_t db0;
+                if (!B_MN) db0 = tc::make_smem_desc(sb, 16, 8 * A_ROW_BYTES, A_LAYOUT);
+                else db0 = tc::make_smem_desc(sb, BMN_SUB_BYTES, 8 * BMN_ROW_BYTES, BMN_LAYOUT);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t da = da0 + (uint64_t)((k * 32) >> 4);
+                  const uint64_t db = B_MN ? db0 + (uint64_t)((k * 16 * BMN_ROW_BYTES) >> 4) : db0 + (uint64_t)((k * 32) >> 4);
+                  tc::umma_bf16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                tc::umma_commit(&empty_bar[s]);
+                if (t == 8) tc::umma_commit(&a_empty_bar[as]);
+                if (i == num_kb - 1) tc::umma_commit(&tmem_full_bar[acc]);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        continue;
+      }
       for (int i = 0; i < num_kb; ++i, ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
+        const int s = ring_s;
+        const uint32_t ph = ring_ph;
+        if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
         tc::mbar_wait(&full_bar[s], ph);
         tc::tc_fence_after();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
           const uint64_t da0 = tc::make_smem_desc(sa, 16, 8 * A_ROW_BYTES, A_LAYOUT);
@@ -314,11 +418,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 
       for (int cj = 0; cj < my_chunks; ++cj) {
         const int chunk = half + 2 * cj;
-        uint8_t* cbuf = out_stage + (size_t)chunk * OUT_CHUNK_BYTES;
-        // the store that used this buffer one tile ago must have finished reading it (bulk groups retire in order)
+        uint8_t* cbuf = out_stage + (size_t)((it % OUT_BUFS) * OUT_CHUNKS + chunk) * OUT_CHUNK_BYTES;
+        // the store that used this buffer OUT_BUFS tiles ago must have finished reading it (bulk groups retire in
+        // order; this thread commits CH groups per tile)
         if (eth == 0) {
-          if (CH <= 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          constexpr int PENDING_OK = OUT_BUFS * CH - 1;
+          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING_OK) : "memory");
         }
         if (cj == 0) my_row_pix[row] = pix;
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -529,7 +634,7 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int ncol0 = blockIdx.x * BN;       // cin tile
   const int m0 = blockIdx.y * 128;         // cout tile
@@ -559,43 +664,52 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(const __grid_consta
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (num_kb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      {
         const CUtensorMap* mA = &p.tmA[tap.srcA];
         const CUtensorMap* mB = &p.tmB[tap.srcB];
         const uint32_t tx_bytes = (uint32_t)p.rows * (uint32_t)(a_row_bytes * p.a_chunks + B_ROW_BYTES * B_SUBS);
+        int ring_s = 0;
+        uint32_t ring_ph = 0;
+        // pixel-tile coordinates advance incrementally (no integer division inside the single-thread issue loop)
+        int tx = kb_begin % p.tiles_x;
+        int ty = (kb_begin / p.tiles_x) % p.tiles_y;
+        int tn = kb_begin / (p.tiles_x * p.tiles_y);
         for (int i = 0; i < num_kb; ++i) {
-          const int kb = kb_begin + i;
-          const int s = i % stages;
-          const uint32_t ph = (i / stages) & 1;
-          const int tx = kb % p.tiles_x;
-          const int ty = (kb / p.tiles_x) % p.tiles_y;
-          const int tn = kb / (p.tiles_x * p.tiles_y);
+          const int s = ring_s;
+          const uint32_t ph = ring_ph;
+          if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
           const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++tn; } }
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          tc::mbar_expect_tx(&full_bar[s], tx_bytes);
-          for (int j = 0; j < p.a_chunks; ++j)
-            tc::tma_load_4d(sa + j * A_SUB_BYTES, mA, &full_bar[s], m0 + j * p.a_cw, x0 + tap.ax, y0 + tap.ay, n0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&full_bar[s], tx_bytes);
+            for (int j = 0; j < p.a_chunks; ++j)
+              tc::tma_load_4d(sa + j * A_SUB_BYTES, mA, &full_bar[s], m0 + j * p.a_cw, x0 + tap.ax, y0 + tap.ay, n0);
 #pragma unroll
-          for (int j = 0; j < B_SUBS; ++j)
-            tc::tma_load_4d(sb + j * B_SUB_BYTES, mB, &full_bar[s], ncol0 + j * B_CW, x0 + tap.bx, y0 + tap.by, n0);
+            for (int j = 0; j < B_SUBS; ++j)
+              tc::tma_load_4d(sb + j * B_SUB_BYTES, mB, &full_bar[s], ncol0 + j * B_CW, x0 + tap.bx, y0 + tap.by, n0);
+          }
         }
       }
     } else if (warp == 1) {
       const int ksteps = p.rows / 16;
       // A: M = 128 = (128 / a_cw) chunks of a_cw channels; chunks beyond a_chunks alias chunk 0 via LBO = 0
       const uint32_t a_lbo = (p.a_chunks * p.a_cw >= 128) ? (uint32_t)A_SUB_BYTES : 0u;
+      int ring_s = 0;
+      uint32_t ring_ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (i / stages) & 1;
+        const int s = ring_s;
+        const uint32_t ph = ring_ph;
+        if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
         tc::mbar_wait(&full_bar[s], ph);
         tc::tc_fence_after();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint32_t sa = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
           const uint64_t da0 = tc::make_smem_desc(sa, a_lbo, 8 * a_row_bytes, a_layout);

@@ -63,10 +63,12 @@ class Plan:
         self.dlogits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
         self.logits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
         self._build()
-        for builder in reversed(self._bwd_builders):
+        self.bwd_tags = []
+        for tag, builder in reversed(self._bwd_builders):
             B = _OpList()
             builder(B)
             self.bwd_layers.append(B)
+            self.bwd_tags.append(tag)
         self.launches_fwd = len(self.fwd_ops)
         self.launches_bwd = sum(len(l) for l in self.bwd_layers)
 
@@ -232,7 +234,7 @@ class Plan:
                 B.add("misc", lambda: stem_gw.zero_())
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1), sflops, _nb(dz0, col))
                 B.add("misc", lambda: ops.stem_unpack_wgrad(stem_gw, stem_g))
-            self._bwd_builders.append(build_stem)
+            self._bwd_builders.append(("stem", build_stem))
 
         # ---- encoder stages (torchvision BasicBlock / Bottleneck)
         x = c1
@@ -240,6 +242,7 @@ class Plan:
         for li, layer in enumerate((enc.layer1, enc.layer2, enc.layer3, enc.layer4)):
             for bi, blk in enumerate(layer):
                 xin = x
+                self._cur_tag = "layer%d" % (li + 1)
                 x = self._res_block(x, blk)
                 self.units.append(("block", "encoder.layer%d.%d" % (li + 1, bi), (xin,), x))
             skips.append(x)
@@ -253,7 +256,7 @@ class Plan:
                 d_pool, d_c5 = self.gbuf(pool), self.gbuf(c5)
                 acc = self.gmode(c5)  # dec5's skip dgrad ran first -> accumulate
                 B.add("maxpool", lambda: ops.maxpool2_bwd(c5, d_pool, d_c5, acc), 0, _nb(c5, d_pool, d_c5))
-            self._bwd_builders.append(build_pool)
+            self._bwd_builders.append(("decoder", build_pool))
         center = self._decoder(pool, None, net.center, pool_input=True)
         d5 = self._decoder(center, c5, net.dec5)
         d4 = self._decoder(d5, c4, net.dec4)
@@ -287,7 +290,7 @@ class Plan:
                 B.add("channel_sum", lambda: ops.channel_sum(g_d0, gb0), 0, _nb(g_d0))
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(g_d0, d1, gw0, 3, 1), f0, _nb(g_d0, d1))
                 self.dgrad_into(B, g_d0, conv0, d1, relu_mask=d1)
-            self._bwd_builders.append(build_head)
+            self._bwd_builders.append(("decoder", build_head))
 
     def _res_block(self, x, blk):
         """torchvision BasicBlock / Bottleneck forward + backward plan"""
@@ -344,7 +347,7 @@ class Plan:
                 if blk.downsample is not None:
                     dzd = self.conv_unit_backward(B, d_out, out, zd, bnd, dconv, x)
                     self.dgrad_into(B, dzd, dconv, x)
-            self._bwd_builders.append(build_block)
+            self._bwd_builders.append((self._cur_tag, build_block))
         return out
 
     def _decoder(self, x1, skip, block, pool_input=False):
@@ -391,7 +394,7 @@ class Plan:
                 self.dgrad_into(B, g_mid, conv, x1, relu_mask=None if pool_input else x1, ci_off=0)
                 if skip is not None:
                     self.dgrad_into(B, g_mid, conv, skip, relu_mask=None, ci_off=c1)
-            self._bwd_builders.append(build_dec)
+            self._bwd_builders.append(("decoder", build_dec))
         return out
 
     # ------------------------------------------------------------------------------------------ execution
@@ -413,11 +416,28 @@ class Plan:
         for op in self.fwd_ops:
             op()
 
-    def _run_bwd(self):
-        self.net._g32.zero_()
-        for layer in self.bwd_layers:  # already in execution (reverse-forward) order
+    def _run_bwd(self, first=0, last=None):
+        """backward layers [first, last) in execution (reverse-forward) order; the gradient arena is zeroed with the
+        first layer"""
+        if first == 0:
+            self.net._g32.zero_()
+        for layer in self.bwd_layers[first:last]:
             for op in layer:
                 op()
+
+    def bwd_segments(self):
+        """split points for overlapping the gradient all-reduce with the backward pass: [decoder | layer4 | rest].
+        -> [(first_layer, last_layer, arena_lo, arena_hi)], arena ranges complete when the segment has run"""
+        net = self.net
+        tags = self.bwd_tags
+        n = len(tags)
+        i_dec = max(i for i, t in enumerate(tags) if t == "decoder") + 1
+        i_l4 = max(i for i, t in enumerate(tags) if t == "layer4") + 1
+        off = {name: net._slots[id(p)].off for name, p, _ in net._arena_params()}
+        total = net._p32.numel()
+        o_dec = off["center.block.0.conv.weight"]
+        o_l4 = off["encoder.layer4.0.conv1.weight"]
+        return [(0, i_dec, o_dec, total), (i_dec, i_l4, o_l4, o_dec), (i_l4, n, 0, o_l4)]
 
     def forward(self, x, use_graph=True):
         self.x_in.copy_(x)

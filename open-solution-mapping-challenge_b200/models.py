@@ -361,6 +361,12 @@ class FusedTrainStep:
         self.use_graphs = os.environ.get("MCB_NO_GRAPH", "0") != "1"
         self.launches = None
         self._staging = None
+        self.segments = None
+        # opt-in: on 2 GPUs the three smaller all-reduces + graph segmentation cost more than they hide (22.8 vs 22.3
+        # ms/step, gpurun r1); kept for larger worlds / slower fabrics
+        if self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "1":
+            self.segments = self.plan.bwd_segments()
+            self._comm_stream = torch.cuda.Stream(device=dev)
 
     # segments ----------------------------------------------------------------------------------------------------
     def _seg_forward(self):
@@ -368,18 +374,29 @@ class FusedTrainStep:
         self.plan._run_fwd()
         ops.loss_partials(self.plan.logits, self.target, self.sums, mode=self.loss_mode, **self.loss_cfg)
 
-    def _seg_backward(self):
-        ops.loss_grad(self.plan.logits, self.target, self.sums, self.plan.dlogits, self.loss,
-                      global_pixels=self.pixels * self.world, mode=self.loss_mode, **self.loss_cfg)
-        self.plan._run_bwd()
+    def _seg_backward(self, seg=None):
+        """seg None: whole backward; else one of plan.bwd_segments() (multi-GPU: the gradient all-reduce of a finished
+        segment overlaps the next segment's kernels)"""
+        if seg is None or seg[0] == 0:
+            ops.loss_grad(self.plan.logits, self.target, self.sums, self.plan.dlogits, self.loss,
+                          global_pixels=self.pixels * self.world, mode=self.loss_mode, **self.loss_cfg)
+        if seg is None:
+            self.plan._run_bwd()
+        else:
+            self.plan._run_bwd(seg[0], seg[1])
 
     def _adam(self, lr, betas, eps, weight_decay):
         net = self.net
         ops.adam_step(net._p32, net._g32, self.m, self.v, net._w16, self.t, lr, betas, eps, weight_decay, 1.0)
 
     def _capture(self):
+        segs = [self._seg_forward]
+        if self.segments is None:
+            segs.append(self._seg_backward)
+        else:
+            segs += [(lambda sg=sg: self._seg_backward(sg)) for sg in self.segments]
         gs = []
-        for seg in (self._seg_forward, self._seg_backward):
+        for seg in segs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 seg()
@@ -422,12 +439,32 @@ class FusedTrainStep:
             self.graphs[0].replay()
         if self.world > 1:
             dist.all_reduce(self.sums)
-        if first or not self.use_graphs:
-            self._seg_backward()
+        eager = first or not self.use_graphs
+        if self.segments is None:
+            if eager:
+                self._seg_backward()
+            else:
+                self.graphs[1].replay()
         else:
-            self.graphs[1].replay()
-        if self.world > 1:
-            dist.all_reduce(self.net._g32)
+            # bucketed gradient all-reduce: segment k's arena range is reduced on the NCCL stream while segment k+1 runs
+            main = torch.cuda.current_stream()
+            works = []
+            for k, sg in enumerate(self.segments):
+                if eager:
+                    self._seg_backward(sg)
+                else:
+                    self.graphs[1 + k].replay()
+                grad_slice = self.net._g32[sg[2]:sg[3]]
+                if k + 1 < len(self.segments):
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    with torch.cuda.stream(self._comm_stream):
+                        self._comm_stream.wait_event(ev)
+                        works.append(dist.all_reduce(grad_slice, async_op=True))
+                else:
+                    works.append(dist.all_reduce(grad_slice, async_op=True))
+            for wk in works:
+                wk.wait()
         self._adam(lr, betas, eps, weight_decay)
         if first:
             torch.cuda.synchronize()
