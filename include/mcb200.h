@@ -69,14 +69,18 @@ typedef struct {
   const void* relu_mask; /* NHWC bf16 like dx or NULL: dx is zeroed where relu_mask <= 0 (backward of the ReLU that
                             produced the conv input) */
   int accumulate;        /* dx += (TMA reduce-add) instead of dx = */
-  /* optional fused BatchNorm-backward reductions for the BN whose ReLU output is this conv's input (dx is then
-     g = dy_in * (relu_mask > 0)):  bn_dbeta[c] += sum g,  bn_dgamma[c] += sum g * (bn_z - bn_mean[c]) * bn_invstd[c];
-     bn_z: NHWC bf16 like dx (the BN input); all NULL to disable */
+  /* optional fused backward of the conv-BatchNorm-ReLU unit whose output is this conv's input (relu_mask must then be
+     NULL: the ReLU mask is that unit's own output sign, recomputed from its BatchNorm input bn_z exactly as the
+     forward did):   y = fma(bn_z, bn_gamma*bn_invstd, bn_beta - bn_mean*bn_gamma*bn_invstd);  g = dy_in * (y > 0);
+     dx = g;  bn_dbeta[c] += sum g;  bn_dgamma[c] += sum g * (bn_z - bn_mean[c]) * bn_invstd[c]   (sums over the
+     STORED bf16 g).  bn_z: NHWC bf16 like dx; all NULL to disable */
   const void* bn_z;
   const float* bn_mean;
   const float* bn_invstd;
   float* bn_dbeta;
   float* bn_dgamma;
+  const float* bn_gamma;
+  const float* bn_beta;
 } mcb_conv_dgrad_args;
 int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream);
 

@@ -26,7 +26,7 @@ class ConvDgradArgs(C.Structure):
     _fields_ = [("dy", vp), ("n", ci), ("h", ci), ("w", ci), ("weight", vp), ("cout", ci), ("cin_total", ci),
                 ("ci_off", ci), ("cin", ci), ("ksize", ci), ("stride", ci), ("dx", vp), ("relu_mask", vp),
                 ("accumulate", ci), ("bn_z", vp), ("bn_mean", vp), ("bn_invstd", vp), ("bn_dbeta", vp),
-                ("bn_dgamma", vp)]
+                ("bn_dgamma", vp), ("bn_gamma", vp), ("bn_beta", vp)]
 
 
 class ConvWgradArgs(C.Structure):

@@ -238,6 +238,7 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
   MCB_REQUIRE(a->ksize == 1 || a->ksize == 3, "conv_dgrad: ksize %d", a->ksize);
   MCB_REQUIRE(a->stride == 1 || a->stride == 2, "conv_dgrad: stride %d", a->stride);
   MCB_REQUIRE(!(a->relu_mask && a->accumulate), "conv_dgrad: relu_mask with accumulate is ill-defined");
+  MCB_REQUIRE(!(a->relu_mask && a->bn_z), "conv_dgrad: with bn_z the mask is derived from bn_z (relu_mask must be NULL)");
   if (int r = check_c(a->cout, "conv_dgrad dy")) return r;
   if (int r = check_c(a->cin, "conv_dgrad dx")) return r;
   const int H = a->h, W = a->w, N = a->n;
@@ -306,22 +307,24 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
     if (int r = encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wb, dims, str, box, bmn_cw * 2)) return r;
   }
   const int out_cw = BN >= 64 ? 64 : 32;
+  const void* aux = a->bn_z ? a->bn_z : a->relu_mask;  // tensor with the geometry of dx, tiled like the output
   for (int ph = 0; ph < phases; ++ph) {
     const int py = (a->stride == 1) ? -1 : (phase_map[ph] >> 1), px = (a->stride == 1) ? -1 : (phase_map[ph] & 1);
     if (int r = encode_nhwc_view(&p.tmD[ph], a->dx, N, H, W, a->cin, 0, a->cin, py, px, out_cw, p.bw, p.bh, p.bn,
                                  out_cw * 2)) return r;
+    if (aux)
+      if (int r = encode_nhwc_view(&p.tmX[ph], aux, N, H, W, a->cin, 0, a->cin, py, px, out_cw, p.bw, p.bh, p.bn,
+                                   out_cw * 2)) return r;
   }
   p.accumulate = a->accumulate;
-  if (a->relu_mask || a->bn_z) {
-    p.mask = static_cast<const __nv_bfloat16*>(a->relu_mask);
-    p.mask_H = H; p.mask_W = W; p.mask_C = a->cin; p.mask_s = a->stride;
-  }
+  p.aux_mode = a->bn_z ? 2 : (a->relu_mask ? 1 : 0);
   if (a->bn_z) {
-    MCB_REQUIRE(a->bn_mean && a->bn_invstd && a->bn_dbeta && a->bn_dgamma, "conv_dgrad: incomplete bn reduction args");
+    MCB_REQUIRE(a->bn_mean && a->bn_invstd && a->bn_gamma && a->bn_beta && a->bn_dbeta && a->bn_dgamma,
+                "conv_dgrad: incomplete bn reduction args");
     MCB_REQUIRE(!a->accumulate, "conv_dgrad: bn reduction needs the complete gradient (no accumulate)");
     MCB_REQUIRE(!(a->stride == 2 && a->ksize == 1), "conv_dgrad: bn reduction with a 1x1 stride-2 conv is unsupported");
-    p.bn_z = static_cast<const __nv_bfloat16*>(a->bn_z);
-    p.bn_mean = a->bn_mean; p.bn_invstd = a->bn_invstd; p.bn_dbeta = a->bn_dbeta; p.bn_dgamma = a->bn_dgamma;
+    p.bn_mean = a->bn_mean; p.bn_invstd = a->bn_invstd; p.bn_gamma = a->bn_gamma; p.bn_beta = a->bn_beta;
+    p.bn_dbeta = a->bn_dbeta; p.bn_dgamma = a->bn_dgamma;
   }
   return launch_conv(BN, BK, true, p, (int)m_tiles, a->cin / BN, phases, st, halo);
 }
@@ -404,8 +407,9 @@ extern "C" int mcb_convt_dgrad(const mcb_convt_dgrad_args* a, void* stream) {
                                out_cw * 2)) return r;
   p.accumulate = a->accumulate;
   if (a->relu_mask) {
-    p.mask = static_cast<const __nv_bfloat16*>(a->relu_mask);
-    p.mask_H = H; p.mask_W = W; p.mask_C = a->cin; p.mask_s = 1;
+    if (int r = encode_nhwc_view(&p.tmX[0], a->relu_mask, N, H, W, a->cin, 0, a->cin, -1, -1, out_cw, p.bw, p.bh, p.bn,
+                                 out_cw * 2)) return r;
+    p.aux_mode = 1;
   }
   return launch_conv(BN, BK, true, p, (int)m_tiles, a->cin / BN, 1, st);
 }
@@ -443,6 +447,15 @@ static int launch_wgrad(WgradParams& p, int cin_src, cudaStream_t st) {
   int splits = (int)std::max(1L, std::min((long)p.tiles_total, cap / std::max(1L, base)));
   const int min_kb = env_int("MCB_WGRAD_MIN_KB", 6);
   splits = std::max(1, std::min(splits, std::max(1, p.tiles_total / min_kb)));
+  // short reductions (deep layers: few pixel tiles, many weights) are bound by the fp32 red.add epilogues, not by the
+  // operand streams: aim for `kb_target` K blocks per CTA, but keep at least a fraction of a wave busy
+  const int kb_target = env_int("MCB_WGRAD_KB_TARGET", 64);
+  if (kb_target > 0) {
+    const long lo_cap = cap * env_int("MCB_WGRAD_MIN_WAVE_X10", 5) / 10;
+    const int lo = (int)std::max(1L, lo_cap / std::max(1L, base));
+    const int want = std::max(1, p.tiles_total / kb_target);
+    splits = std::max(1, std::min(splits, std::max(lo, want)));
+  }
   int forced = env_int("MCB_WGRAD_SPLITS", 0);
   if (forced > 0) splits = std::min(forced, p.tiles_total);
   p.splits = splits;

@@ -48,15 +48,21 @@ struct ConvGemmParams {
   const float* bias;
   float* stats;
   int stats_c;  // number of channels in stats (cout)
-  const __nv_bfloat16* mask;  // ReLU mask tensor (NHWC, full-resolution output tensor), or null
-  int mask_H, mask_W, mask_C, mask_s;  // full dims; mask_s = 1 (plain) or 2 (output is a parity view)
+  int mask_H, mask_W, mask_C, mask_s;  // geometry of `residual`: full dims; mask_s = 1 (plain) or 2 (parity view)
   int relu;
   int accumulate;
-  // fused BatchNorm-backward reductions (dgrad only): with g = the stored (masked) output gradient,
-  // dbeta += sum g, dgamma += sum g * (z - mean) * invstd; z has the geometry of `mask`
-  const __nv_bfloat16* bn_z;
+  // Auxiliary tile (dgrad only): a tensor with the geometry of the OUTPUT, fetched chunk by chunk with TMA (tmX, same
+  // boxes as tmD) into shared memory while the main loop of the tile still runs.
+  //   aux_mode 1: the ReLU output y of the producing layer:  g = acc * (y > 0)
+  //   aux_mode 2: the BatchNorm input z of the producing conv-BN-ReLU unit: the mask is that unit's own output sign,
+  //               (fma(z, gamma*invstd, beta - mean*gamma*invstd) > 0), and the BatchNorm-backward reductions of the
+  //               stored gradient ride along:  dbeta += sum g,  dgamma += sum g * (z - mean) * invstd
+  CUtensorMap tmX[4];
+  int aux_mode;
   const float* bn_mean;
   const float* bn_invstd;
+  const float* bn_gamma;
+  const float* bn_beta;
   float* bn_dbeta;
   float* bn_dgamma;
 };
@@ -141,7 +147,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint64_t* a_full_bar = tmem_empty_bar + 2;      // [2] (HALO)
   uint64_t* a_empty_bar = a_full_bar + 2;         // [2] (HALO)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty_bar + 2);
+  uint64_t* aux_full_bar = a_empty_bar + 2;       // [2] one per epilogue half
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full_bar + 2);
   int* row_pix = reinterpret_cast<int*>(tmem_slot + 2);  // [2][128] pixel index in the full-resolution tensor, -1 = invalid
 
   // the shuffle makes the warp index provably warp-uniform, so the role loops below compile onto the uniform datapath
@@ -164,6 +171,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tc::mbar_init(&a_full_bar[1], 1);
     tc::mbar_init(&a_empty_bar[0], 1);
     tc::mbar_init(&a_empty_bar[1], 1);
+    tc::mbar_init(&aux_full_bar[0], 1);
+    tc::mbar_init(&aux_full_bar[1], 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&p.tmB);
     tc::prefetch_tmap(&p.tmA[0]);
@@ -357,21 +366,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     const int wi = row % p.bw;
     const int hi = (row / p.bw) % p.bh;
     const int ni = row / (p.bw * p.bh);
-    const int my_chunks = (OUT_CHUNKS > half) ? (OUT_CHUNKS - half + 1) / 2 : 0;
+    // single-chunk tiles (BN <= 64): the halves alternate TILES instead (half h drains tiles with it % 2 == h, i.e. its
+    // own TMEM accumulator), so two epilogues are in flight at once where the per-tile main loop is shortest
+    constexpr bool ALT = (OUT_CHUNKS == 1);
+    const int my_chunks = ALT ? 1 : (OUT_CHUNKS - half + 1) / 2;
     // per-channel reductions are kept in registers (threads eth < OUT_CW, one channel per chunk) across all tiles of
     // this CTA that share an N tile, and flushed with one atomic per channel when the N tile changes / at the end
     float racc1[CH], racc2[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) racc1[j] = racc2[j] = 0.f;
     int racc_nt = -1;
-    const bool do_red = (p.stats != nullptr || p.bn_z != nullptr);
+    const int aux_mode = p.aux_mode;
+    const bool do_red = (p.stats != nullptr || aux_mode == 2);
+    // aux modes use the four chunk buffers as {out[half], aux[half]}
+    uint8_t* abuf = out_stage + (size_t)(2 + half) * OUT_CHUNK_BYTES;
+    uint32_t aux_n = 0;
+    auto issue_aux = [&](int t2, int chunk2) {   // one thread: fetch the aux chunk of tile t2 into abuf
+      const int ph2 = t2 % p.phases;
+      const int mt2 = (t2 / p.phases) % p.m_tiles;
+      const int nt2 = t2 / (p.phases * p.m_tiles);
+      const int tx2 = mt2 % p.tiles_x, ty2 = (mt2 / p.tiles_x) % p.tiles_y, tn2 = mt2 / (p.tiles_x * p.tiles_y);
+      tc::mbar_expect_tx(&aux_full_bar[half], (uint32_t)p.rows * OUT_ROW_BYTES);
+      tc::tma_load_4d(abuf, &p.tmX[ph2], &aux_full_bar[half], p.n_off + nt2 * BN + chunk2 * OUT_CW, tx2 * p.bw,
+                      ty2 * p.bh, tn2 * p.bn);
+    };
+    if (aux_mode != 0 && eth == 0) {
+      const int t0 = blockIdx.x + (ALT ? half * gridDim.x : 0);
+      if (t0 < total_tiles) issue_aux(t0, ALT ? 0 : half);
+    }
     auto flush_reductions = [&]() {
       if (racc_nt >= 0 && eth < OUT_CW) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           if (j < my_chunks) {
-            const int ch = p.n_off + racc_nt * BN + (half + 2 * j) * OUT_CW + eth;
-            if (p.bn_z == nullptr) {
+            const int ch = p.n_off + racc_nt * BN + (ALT ? 0 : half + 2 * j) * OUT_CW + eth;
+            if (aux_mode != 2) {
               atomicAdd(p.stats + ch, racc1[j]);
               atomicAdd(p.stats + p.stats_c + ch, racc2[j]);
             } else {
@@ -394,6 +423,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int ox = x0 + wi, oy = y0 + hi, on = n0 + ni;
       const bool valid = row < p.rows && ox < p.Wv && oy < p.Hv && on < p.Nimg;
       const int acc = it & 1;
+      if (ALT && acc != half) {
+        // not this half's tile: only keep the accumulator hand-off in lock-step (8 arrivals per tile)
+        tc::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+        tc::tc_fence_before();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       if (do_red && nt != racc_nt) {
         flush_reductions();
         racc_nt = nt;
@@ -407,8 +443,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           pix = (on * p.mask_H + fy) * p.mask_W + fx;
         }
       }
-      const __nv_bfloat16* mrow = nullptr;
-      if (p.mask != nullptr && valid) mrow = p.mask + (size_t)pix * p.mask_C + p.n_off + ncol0;
       const __nv_bfloat16* rrow = nullptr;
       if (p.residual != nullptr && valid) rrow = p.residual + (size_t)pix * p.mask_C + p.n_off + ncol0;
 
@@ -417,13 +451,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 
       for (int cj = 0; cj < my_chunks; ++cj) {
-        const int chunk = half + 2 * cj;
-        uint8_t* cbuf = out_stage + (size_t)((it % OUT_BUFS) * OUT_CHUNKS + chunk) * OUT_CHUNK_BYTES;
+        const int chunk = ALT ? 0 : half + 2 * cj;
+        uint8_t* cbuf = aux_mode != 0 ? out_stage + (size_t)half * OUT_CHUNK_BYTES
+                                      : out_stage + (size_t)((it % OUT_BUFS) * OUT_CHUNKS + chunk) * OUT_CHUNK_BYTES;
         // the store that used this buffer OUT_BUFS tiles ago must have finished reading it (bulk groups retire in
         // order; this thread commits CH groups per tile)
         if (eth == 0) {
-          constexpr int PENDING_OK = OUT_BUFS * CH - 1;
-          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING_OK) : "memory");
+          // (ALT: this half stores every other tile, so OUT_BUFS tiles ago = OUT_BUFS / 2 of its own groups)
+          constexpr int PENDING_OK = ALT ? OUT_BUFS / 2 - 1 : OUT_BUFS * CH - 1;
+          if (aux_mode != 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // single out buffer
+          else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING_OK) : "memory");
         }
         if (cj == 0) my_row_pix[row] = pix;
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -471,21 +508,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (mrow != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(mrow + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 m = __ldg(mp + j);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // bf16 > 0  <=>  sign bit clear and magnitude nonzero
-                const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
-                if (!(lo != 0 && lo < 0x8000u)) f[j * 8 + e * 2] = 0.f;
-                if (!(hi2 != 0 && hi2 < 0x8000u)) f[j * 8 + e * 2 + 1] = 0.f;
-              }
-            }
-          }
           uint8_t* rowp = cbuf + (size_t)row * OUT_ROW_BYTES;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -508,20 +530,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         tc::fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 
-        if (p.stats != nullptr || p.bn_z != nullptr) {
-          // Per-channel reductions over the valid rows of the STORED (bf16) chunk: 16-byte smem reads,
-          // thread = (row group, 8-channel group); row groups are combined through shared memory.
-          //   forward: (sum v, sum v^2)       -> BatchNorm batch statistics of the following layer
-          //   dgrad:   (sum g, sum g * xhat)  -> dbeta / dgamma of the BatchNorm that produced this conv's input
-          const bool bnred = p.bn_z != nullptr;
+        if (do_red || aux_mode != 0) {
+          // Second pass over the STORED (bf16) chunk in a (row group, 8-channel group) layout: 16-byte smem accesses,
+          // per-channel coefficients in registers.
+          //   forward:  (sum v, sum v^2) of the valid rows -> BatchNorm batch statistics of the following layer
+          //   aux 1:    g = v * (y > 0), written back in place
+          //   aux 2:    g = v * (bn(z) > 0) written back, (sum g, sum g * xhat) -> dbeta / dgamma of that BatchNorm
+          if (aux_mode != 0) {
+            tc::mbar_wait(&aux_full_bar[half], aux_n & 1);
+            ++aux_n;
+          }
+          const bool bnred = aux_mode == 2;
           const int cg = eth % CGc, rg = eth / CGc;
           const int ch0 = p.n_off + ncol0 + chunk * OUT_CW + cg * 8;
-          float s1[8], s2[8], mu[8], is[8];
+          float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             s1[j] = s2[j] = 0.f;
             mu[j] = bnred ? __ldg(p.bn_mean + ch0 + j) : 0.f;
             is[j] = bnred ? __ldg(p.bn_invstd + ch0 + j) : 0.f;
+            sc[j] = bnred ? __ldg(p.bn_gamma + ch0 + j) * is[j] : 0.f;       // same expressions as the forward's
+            sh[j] = bnred ? __ldg(p.bn_beta + ch0 + j) - mu[j] * sc[j] : 0.f;  // bn_train_coef (elementwise.cu)
           }
 #pragma unroll
           for (int rr = 0; rr < ROWSc; ++rr) {
@@ -531,47 +560,67 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             int unit = cg;
             if (OUT_CW == 64) unit ^= (r & 7);
             else unit ^= ((r >> 1) & 3);
-            const uint4 pk = *reinterpret_cast<const uint4*>(cbuf + (size_t)r * OUT_ROW_BYTES + unit * 16);
+            const size_t off = (size_t)r * OUT_ROW_BYTES + unit * 16;
+            const uint4 pk = *reinterpret_cast<const uint4*>(cbuf + off);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-            if (!bnred) {
+            if (aux_mode == 0) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 xy = __bfloat1622float2(h2[j]);
                 s1[2 * j] += xy.x; s2[2 * j] += xy.x * xy.x;
                 s1[2 * j + 1] += xy.y; s2[2 * j + 1] += xy.y * xy.y;
               }
+            } else if (aux_mode == 1) {
+              const uint4 ak = *reinterpret_cast<const uint4*>(abuf + off);
+              const uint32_t w[4] = {ak.x, ak.y, ak.z, ak.w};
+              uint32_t o[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // bf16 > 0  <=>  sign bit clear and magnitude nonzero
+                const uint32_t lo = w[e] & 0xFFFFu, hi2 = w[e] >> 16;
+                if (!(lo != 0 && lo < 0x8000u)) o[e] &= 0xFFFF0000u;
+                if (!(hi2 != 0 && hi2 < 0x8000u)) o[e] &= 0x0000FFFFu;
+              }
+              *reinterpret_cast<uint4*>(cbuf + off) = make_uint4(o[0], o[1], o[2], o[3]);
             } else {
-              const uint4 zk = __ldg(reinterpret_cast<const uint4*>(p.bn_z + (size_t)rp * p.mask_C + ch0));
+              const uint4 zk = *reinterpret_cast<const uint4*>(abuf + off);
               const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zk);
+              uint32_t o[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 g = __bfloat1622float2(h2[j]);
+                float2 g = __bfloat1622float2(h2[j]);
                 const float2 zz = __bfloat1622float2(z2[j]);
+                if (!(fmaf(zz.x, sc[2 * j], sh[2 * j]) > 0.f)) { g.x = 0.f; o[j] &= 0xFFFF0000u; }
+                if (!(fmaf(zz.y, sc[2 * j + 1], sh[2 * j + 1]) > 0.f)) { g.y = 0.f; o[j] &= 0x0000FFFFu; }
                 s1[2 * j] += g.x; s2[2 * j] += g.x * ((zz.x - mu[2 * j]) * is[2 * j]);
                 s1[2 * j + 1] += g.y; s2[2 * j + 1] += g.y * ((zz.y - mu[2 * j + 1]) * is[2 * j + 1]);
               }
+              *reinterpret_cast<uint4*>(cbuf + off) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
-          // combine the row groups of this warp with shuffles (lanes l, l+CGc, ... share a channel group), then the
-          // four warps through a small shared-memory table
-#pragma unroll
-          for (int off = CGc; off < 32; off <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-              s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-            }
-          }
+          if (aux_mode != 0) tc::fence_proxy_async_smem();  // the masked chunk is read by the TMA store below
           const int wq = eth >> 5;  // warp inside the half
-          if (lane < CGc) {
-            float4* sc = reinterpret_cast<float4*>(my_scratch + ((size_t)wq * CGc + lane) * 16);
-            sc[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
-            sc[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
-            sc[2] = make_float4(s1[4], s2[4], s1[5], s2[5]);
-            sc[3] = make_float4(s1[6], s2[6], s1[7], s2[7]);
+          if (do_red) {
+            // combine the row groups of this warp with shuffles (lanes l, l+CGc, ... share a channel group), then the
+            // four warps through a small shared-memory table
+#pragma unroll
+            for (int off = CGc; off < 32; off <<= 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+              }
+            }
+            if (lane < CGc) {
+              float4* scq = reinterpret_cast<float4*>(my_scratch + ((size_t)wq * CGc + lane) * 16);
+              scq[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
+              scq[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
+              scq[2] = make_float4(s1[4], s2[4], s1[5], s2[5]);
+              scq[3] = make_float4(s1[6], s2[6], s1[7], s2[7]);
+            }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (eth < OUT_CW) {
+          if (do_red && eth < OUT_CW) {
             float a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int w4 = 0; w4 < 4; ++w4) {
@@ -590,12 +639,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (p.accumulate) tc::tma_reduce_add_4d(mD, cbuf, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
           else tc::tma_store_4d(mD, cbuf, p.n_off + ncol0 + chunk * OUT_CW, x0, y0, n0);
           tc::tma_store_commit();
+          if (aux_mode != 0) {
+            // abuf is free (every thread of the half passed the barrier after its last read): fetch the next chunk
+            if (cj + 1 < my_chunks) issue_aux(t, chunk + 2);
+            else {
+              const int t2 = t + (int)gridDim.x * (ALT ? 2 : 1);
+              if (t2 < total_tiles) issue_aux(t2, ALT ? 0 : half);
+            }
+          }
         }
-      }
-      if (my_chunks == 0) {
-        // nothing to drain for this half (BN <= 64), but stay in lock-step with the accumulator hand-off
-        tc::tc_fence_before();
-        if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
     if (do_red) flush_reductions();

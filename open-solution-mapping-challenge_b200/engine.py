@@ -183,7 +183,8 @@ class Plan:
         red = None
         if bn_reduce is not None:
             zz, bb = bn_reduce
-            red = (zz, bb.mean, bb.invstd, bb.dbeta, bb.dgamma)
+            red = (zz, bb.mean, bb.invstd, bb.gamma, bb.beta, bb.dbeta, bb.dgamma)
+            relu_mask = None  # recomputed from z in the epilogue
         B.add("conv_dgrad", lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
                                                    accumulate=acc, out=gx, bn_reduce=red),
               2.0 * dz.numel() * cin * k * k,
@@ -340,7 +341,7 @@ class Plan:
                 conv_next = conv_l
                 for conv, xin, y, z, bn in reversed(units):
                     # y has a single consumer: its ReLU mask and its BN's backward reductions ride in the dgrad epilogue
-                    self.dgrad_into(B, dz, conv_next, y, relu_mask=y, bn_reduce=(z, bn))
+                    self.dgrad_into(B, dz, conv_next, y, bn_reduce=(z, bn))
                     dz = self.conv_unit_backward(B, self.gbuf(y), None, z, bn, conv, xin, reduced=True)
                     conv_next = conv
                 self.dgrad_into(B, dz, conv_next, x)

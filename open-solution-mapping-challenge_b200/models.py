@@ -370,8 +370,11 @@ class FusedTrainStep:
 
     # segments ----------------------------------------------------------------------------------------------------
     def _seg_forward(self):
-        self.sums.zero_()
         self.plan._run_fwd()
+
+    def _loss_partials(self):
+        # outside the graphs: it is the first reader of the target, whose H2D copy overlaps the forward segment
+        self.sums.zero_()
         ops.loss_partials(self.plan.logits, self.target, self.sums, mode=self.loss_mode, **self.loss_cfg)
 
     def _seg_backward(self, seg=None):
@@ -405,38 +408,47 @@ class FusedTrainStep:
 
     def _stage_inputs(self, X, target):
         """host batches go through a copy stream into double-buffered staging tensors so that the H2D transfer of
-        step i+1 overlaps the compute of step i; device batches are copied directly"""
+        step i+1 overlaps the compute of step i, and the target's transfer overlaps the forward pass of its own step
+        (the loss is its first reader); device batches are copied directly.  Returns a callable that makes the target
+        visible to the current stream (call it after launching the forward)."""
         cur = torch.cuda.current_stream()
         if X.is_cuda and target.is_cuda:
             self.plan.x_in.copy_(X, non_blocking=True)
             self.target.copy_(target, non_blocking=True)
-            return
+            return lambda: None
         if self._staging is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
             self._staging = [(torch.empty_like(self.plan.x_in), torch.empty_like(self.target),
-                              torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
+                              torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()) for _ in range(2)]
             self._stage_i = 0
-        sx, st, ev_loaded, ev_consumed = self._staging[self._stage_i]
+        sx, st, ev_x, ev_t, ev_consumed = self._staging[self._stage_i]
         self._stage_i ^= 1
         cs = self._copy_stream
         cs.wait_event(ev_consumed)  # the compute stream finished reading this slot (no-op before first use)
         with torch.cuda.stream(cs):
             sx.copy_(X.float() if X.dtype != torch.float32 else X, non_blocking=True)
+            ev_x.record(cs)
             st.copy_(target.float() if target.dtype != torch.float32 else target, non_blocking=True)
-            ev_loaded.record(cs)
-        cur.wait_event(ev_loaded)
+            ev_t.record(cs)
+        cur.wait_event(ev_x)
         self.plan.x_in.copy_(sx, non_blocking=True)
-        self.target.copy_(st, non_blocking=True)
-        ev_consumed.record(cur)
+
+        def finish_target():
+            cur.wait_event(ev_t)
+            self.target.copy_(st, non_blocking=True)
+            ev_consumed.record(cur)
+        return finish_target
 
     def step(self, X, target, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        self._stage_inputs(X, target)
+        finish_target = self._stage_inputs(X, target)
         self.t += 1
         first = self.graphs is None and self.use_graphs
         if first or not self.use_graphs:
             self._seg_forward()
         else:
             self.graphs[0].replay()
+        finish_target()
+        self._loss_partials()
         if self.world > 1:
             dist.all_reduce(self.sums)
         eager = first or not self.use_graphs

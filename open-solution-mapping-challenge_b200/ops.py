@@ -65,8 +65,9 @@ def conv_fwd(x, w, ksize, stride=1, bias=None, relu=False, stats=None, x2=None, 
 
 def conv_dgrad(dy, w, ksize, stride, in_hw, cin=None, ci_off=0, relu_mask=None, accumulate=False, out=None,
                bn_reduce=None):
-    """bn_reduce = (z, mean, invstd, dbeta, dgamma): fuse the BatchNorm-backward reductions of the layer that produced
-    this conv's input into the epilogue"""
+    """bn_reduce = (z, mean, invstd, gamma, beta, dbeta, dgamma): fuse the backward of the conv-BN-ReLU unit that
+    produced this conv's input into the epilogue (ReLU mask recomputed from z, BatchNorm-backward reductions);
+    relu_mask must then be None"""
     _chk(dy); _chk(w)
     n = dy.shape[0]
     h, wd = in_hw
@@ -83,8 +84,9 @@ def conv_dgrad(dy, w, ksize, stride, in_hw, cin=None, ci_off=0, relu_mask=None, 
     a.relu_mask = _chk(relu_mask).data_ptr() if relu_mask is not None else None
     a.accumulate = int(accumulate)
     if bn_reduce is not None:
-        z, mean, invstd, dbeta, dgamma = bn_reduce
+        z, mean, invstd, gamma, beta, dbeta, dgamma = bn_reduce
         a.bn_z = _chk(z).data_ptr(); a.bn_mean = mean.data_ptr(); a.bn_invstd = invstd.data_ptr()
+        a.bn_gamma = gamma.data_ptr(); a.bn_beta = beta.data_ptr()
         a.bn_dbeta = dbeta.data_ptr(); a.bn_dgamma = dgamma.data_ptr()
     L.call("mcb_conv_dgrad", a)
     return out

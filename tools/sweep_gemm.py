@@ -45,6 +45,27 @@ def dgrad(cin, cout, k, hw):
     return (lambda: ops.conv_dgrad(dy, w, k, 1, (hw, hw), out=dx)), fl
 
 
+def dgrad_fused(cin, cout, k, hw):
+    """the backward's real epilogue: ReLU mask of the producer + its BatchNorm-backward reductions"""
+    dy, w = mk(N, hw, hw, cout), mk(k * k, cout, cin)
+    dx = torch.empty(N, hw, hw, cin, dtype=BF, device=dev)
+    z = mk(N, hw, hw, cin)
+    mean, invstd = torch.zeros(cin, device=dev), torch.ones(cin, device=dev)
+    gamma, beta = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
+    dbeta, dgamma = torch.zeros(cin, device=dev), torch.zeros(cin, device=dev)
+    fl = 2.0 * N * hw * hw * cin * cout * k * k
+    return (lambda: ops.conv_dgrad(dy, w, k, 1, (hw, hw), out=dx,
+                                   bn_reduce=(z, mean, invstd, gamma, beta, dbeta, dgamma))), fl
+
+
+def dgrad_mask(cin, cout, k, hw):
+    dy, w = mk(N, hw, hw, cout), mk(k * k, cout, cin)
+    dx = torch.empty(N, hw, hw, cin, dtype=BF, device=dev)
+    y = mk(N, hw, hw, cin)
+    fl = 2.0 * N * hw * hw * cin * cout * k * k
+    return (lambda: ops.conv_dgrad(dy, w, k, 1, (hw, hw), out=dx, relu_mask=y)), fl
+
+
 def wgrad(cin, cout, k, hw):
     dy, x = mk(N, hw, hw, cout), mk(N, hw, hw, cin)
     dw = torch.zeros(k * k, cout, cin, device=dev)
@@ -53,7 +74,7 @@ def wgrad(cin, cout, k, hw):
 
 
 SHAPES = [(256, 1024, 1, 20), (1024, 256, 1, 20), (256, 256, 3, 20), (128, 128, 3, 160), (32, 32, 3, 320),
-          (64, 256, 1, 80), (512, 512, 3, 10), (128, 128, 3, 40)]
+          (64, 256, 1, 80), (512, 512, 3, 10), (128, 128, 3, 40), (64, 64, 3, 80), (256, 64, 1, 80)]
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 
@@ -75,12 +96,15 @@ def run(kind, maker, envs):
 
 
 if which in ("all", "fwd"):
-    envs = [{}, {"MCB_MAX_STAGES": 3}, {"MCB_MAX_STAGES": 8}, {"MCB_FORCE_BN": 128}, {"MCB_FORCE_BN": 64}]
+    envs = [{}, {"MCB_FORCE_BN": 128}, {"MCB_FORCE_BN": 64}]
     print("fwd   envs:", envs)
     run("fwd", fwd, envs)
-    run("dgrad", dgrad, envs[:3])
+    run("dgrad", dgrad, envs[:1])
+    run("dgradF", dgrad_fused, envs[:1])
+    run("dgradM", dgrad_mask, envs[:1])
 if which in ("all", "wgrad"):
-    envs = [{}, {"MCB_WGRAD_WAVES_X10": 5}, {"MCB_WGRAD_WAVES_X10": 20}, {"MCB_WGRAD_MIN_KB": 2}, {"MCB_WGRAD_MIN_KB": 16},
-            {"MCB_WGRAD_SPLITS": 1}, {"MCB_WGRAD_SPLITS": 8}, {"MCB_WGRAD_SPLITS": 32}, {"MCB_WGRAD_SPLITS": 128}]
+    envs = [{}, {"MCB_WGRAD_WAVES_X10": 5}, {"MCB_WGRAD_KB_TARGET": 32}, {"MCB_WGRAD_KB_TARGET": 64},
+            {"MCB_WGRAD_KB_TARGET": 128}, {"MCB_WGRAD_KB_TARGET": 64, "MCB_WGRAD_MIN_WAVE_X10": 3},
+            {"MCB_WGRAD_KB_TARGET": 128, "MCB_WGRAD_MIN_WAVE_X10": 3}, {"MCB_WGRAD_KB_TARGET": 128, "MCB_WGRAD_MIN_WAVE_X10": 2}]
     print("wgrad envs:", envs)
     run("wgrad", wgrad, envs)
