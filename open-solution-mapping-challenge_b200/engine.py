@@ -7,6 +7,7 @@ Backward mirrors torch autograd of /root/reference/src/unet_models.py:385-403: p
 (dbeta, dgamma with the ReLU mask folded in), one elementwise pass producing dz, then the tcgen05 dgrad and
 split-K wgrad GEMMs; decoder ReLU masks are applied in the dgrad epilogues; skip-connection gradients are
 accumulated with TMA reduce-add."""
+import os
 import torch
 from torch import nn
 
@@ -31,10 +32,19 @@ def _nb(*tensors):
     return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
 
 
+_SIDE_KINDS = frozenset(("conv_wgrad", "convt_wgrad"))
+
+
 class _OpList(list):
     """list of _Op; .add(kind, fn, flops, bytes)"""
 
+    # profiling aid (tools/knockout.sh): MCB_KNOCKOUT="kind,kind" drops those launches from the plan so that the step-time
+    # difference gives their in-graph cost (results are garbage; never set outside profiling)
+    _knockout = frozenset(k for k in os.environ.get("MCB_KNOCKOUT", "").split(",") if k)
+
     def add(self, kind, fn, flops=0.0, nbytes=0.0, desc=""):
+        if kind in self._knockout:
+            return
         self.append(_Op(kind, fn, flops, nbytes, desc))
 
 
@@ -59,6 +69,7 @@ class Plan:
         self._stats_arena = torch.zeros(2 * total_c, dtype=F32, device=self.dev)
         self._stats_used = 0
         self.graph_fwd = self.graph_bwd = None
+        self._side = None
         self.x_in = torch.zeros((n, 3, h, w), dtype=F32, device=self.dev)
         self.dlogits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
         self.logits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
@@ -422,9 +433,48 @@ class Plan:
         first layer"""
         if first == 0:
             self.net._g32.zero_()
+        # Weight/bias-gradient launches are leaves of the backward graph (they only add into the gradient arena): they
+        # go to a side stream, forked after their producer and joined at the end, so the tensor-core-bound wgrad GEMMs
+        # overlap the HBM-bound BatchNorm-backward kernels of the layers below instead of queueing behind them.
+        # (No buffer is recycled inside a step, so the only hazards are the recorded producer -> consumer edges.)
+        use_side = os.environ.get("MCB_SIDE_WGRAD", "1") == "1"
+        main = torch.cuda.current_stream()
+        if use_side and self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        forked = False
+        pending = []
+        defer = os.environ.get("MCB_SIDE_DEFER", "1") == "1"
+
+        def flush():
+            nonlocal forked
+            if not pending:
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                for q in pending:
+                    q()
+            pending.clear()
+            forked = True
+
         for layer in self.bwd_layers[first:last]:
             for op in layer:
-                op()
+                if use_side and op.kind in _SIDE_KINDS and op.desc:
+                    pending.append(op)
+                    if not defer:
+                        flush()
+                else:
+                    op()
+                    # a deferred wgrad starts right AFTER the next data-gradient GEMM (which needs whole SMs), i.e.
+                    # next to the BatchNorm-backward kernels that follow it
+                    if op.kind in ("conv_dgrad", "convt_dgrad"):
+                        flush()
+        flush()
+        if forked:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            main.wait_event(ev)
 
     def bwd_segments(self):
         """split points for overlapping the gradient all-reduce with the backward pass: [decoder | layer4 | rest].
