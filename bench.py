@@ -285,15 +285,25 @@ def main():
     loss_dev = float(last["loss"])
     note("device arm timed: %.3f ms/step" % ms_dev)
 
-    # ---- end-to-end arm: pinned host batches in, loss read back each step (one step of pipelining: the loss of
-    # step i is read after step i+1 has been enqueued, so the H2D copy of the next batch overlaps compute)
-    prev = {"loss": None}
+    # ---- end-to-end arm: pinned host batches in, loss read back EVERY step.  One step of pipelining: the D2H copy of
+    # step i's loss is enqueued (into pinned memory, followed by an event) right behind step i, and the host consumes it
+    # after it has enqueued step i+1 -- so the H2D copy of the next batch and the host-side launch work overlap compute.
+    # (A plain loss.cpu() of the previous step would be stream-ordered behind the step just enqueued and stall the host
+    # for a whole step: tools/dbg_e2e.py.)
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    prev = {"i": 0, "pending": False}
 
     def step_e2e():
+        i = prev["i"]
         cur = model._fit_loop([Xh, Th])["sum"]
-        if prev["loss"] is not None:
-            prev["val"] = float(prev["loss"].cpu())
-        prev["loss"] = cur
+        loss_host[i & 1].copy_(cur, non_blocking=True)
+        loss_ev[i & 1].record()
+        if prev["pending"]:
+            loss_ev[(i - 1) & 1].synchronize()
+            prev["val"] = float(loss_host[(i - 1) & 1])
+        prev["pending"] = True
+        prev["i"] = i + 1
 
     for _ in range(args.warmup):
         step_e2e()
@@ -323,7 +333,7 @@ def main():
                    "loss_last_step": loss_dev},
         "e2e": {"value": round(e2e, 2), "unit": "tiles/s", "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": int(Xh.numel() * 4 + Th.numel() * 4), "d2h_bytes_per_step": 4,
-                "api": "mcb200.models.PyTorchUNetWeighted._fit_loop([X_host_pinned, target_host_pinned]) + loss.cpu()"},
+                "api": "mcb200.models.PyTorchUNetWeighted._fit_loop([X_host_pinned, target_host_pinned]) + async D2H of the loss into pinned memory, consumed one step later"},
         "gpu_launches": fused.count_launches() * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",

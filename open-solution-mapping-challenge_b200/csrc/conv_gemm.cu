@@ -48,7 +48,7 @@ static int launch_conv_inst(const ConvGemmParams& p, dim3 grid, size_t smem, cud
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, BK, B_MN, HALO><<<grid, kConvThreads, smem, st>>>(p);
+  launch_pdl(conv_gemm_kernel<BN, BK, B_MN, HALO>, grid, kConvThreads, smem, st, p);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }
@@ -424,7 +424,7 @@ static int launch_wgrad_inst(const WgradParams& p, dim3 grid, size_t smem, cudaS
     MCB_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  wgrad_kernel<BN><<<grid, kGemmThreads, smem, st>>>(p);
+  launch_pdl(wgrad_kernel<BN>, grid, kGemmThreads, smem, st, p);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_prologue();  // everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
@@ -716,6 +717,7 @@ __global__ void __launch_bounds__(kGemmThreads) wgrad_kernel(const __grid_consta
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_prologue();  // everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (num_kb > 0) {

@@ -96,11 +96,11 @@ def run(kind, maker, envs):
 
 
 if which in ("all", "fwd"):
-    envs = [{}, {"MCB_FORCE_BN": 128}, {"MCB_FORCE_BN": 64}]
+    envs = [{}, {"MCB_HALO": 1}]
     print("fwd   envs:", envs)
     run("fwd", fwd, envs)
-    run("dgrad", dgrad, envs[:1])
-    run("dgradF", dgrad_fused, envs[:1])
+    run("dgrad", dgrad, envs)
+    run("dgradF", dgrad_fused, envs)
     run("dgradM", dgrad_mask, envs[:1])
 if which in ("all", "wgrad"):
     envs = [{}, {"MCB_WGRAD_WAVES_X10": 5}, {"MCB_WGRAD_KB_TARGET": 32}, {"MCB_WGRAD_KB_TARGET": 64},
