@@ -187,7 +187,24 @@ def evs_bwd_started(evs):
     return True
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else this process (or NCCL's banner, printed from C) writes
+    to fd 1 has been rerouted to stderr by main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -219,7 +236,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -355,7 +372,7 @@ def main():
         cb = cpu_reference_arm(args, sample_batch=2, steps=2, warmup=1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         note("cpu baseline done")
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -81,6 +81,8 @@ typedef struct {
   float* bn_dgamma;
   const float* bn_gamma;
   const float* bn_beta;
+  float* dx_channel_sum; /* fp32 [cin] or NULL (needs relu_mask, no accumulate): += sum over pixels of the stored dx, i.e.
+                            the bias gradient of the conv+bias+ReLU layer that produced this conv's input */
 } mcb_conv_dgrad_args;
 int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream);
 
@@ -115,6 +117,7 @@ typedef struct {
   void* dx;           /* NHWC bf16 [n][h][w][cin] */
   const void* relu_mask;
   int accumulate;
+  float* dx_channel_sum; /* as in mcb_conv_dgrad_args */
 } mcb_convt_dgrad_args;
 int mcb_convt_dgrad(const mcb_convt_dgrad_args* a, void* stream);
 

@@ -26,7 +26,7 @@ class ConvDgradArgs(C.Structure):
     _fields_ = [("dy", vp), ("n", ci), ("h", ci), ("w", ci), ("weight", vp), ("cout", ci), ("cin_total", ci),
                 ("ci_off", ci), ("cin", ci), ("ksize", ci), ("stride", ci), ("dx", vp), ("relu_mask", vp),
                 ("accumulate", ci), ("bn_z", vp), ("bn_mean", vp), ("bn_invstd", vp), ("bn_dbeta", vp),
-                ("bn_dgamma", vp), ("bn_gamma", vp), ("bn_beta", vp)]
+                ("bn_dgamma", vp), ("bn_gamma", vp), ("bn_beta", vp), ("dx_channel_sum", vp)]
 
 
 class ConvWgradArgs(C.Structure):
@@ -41,7 +41,7 @@ class ConvtFwdArgs(C.Structure):
 
 class ConvtDgradArgs(C.Structure):
     _fields_ = [("dy", vp), ("n", ci), ("h", ci), ("w", ci), ("cin", ci), ("weight", vp), ("cout", ci), ("dx", vp),
-                ("relu_mask", vp), ("accumulate", ci)]
+                ("relu_mask", vp), ("accumulate", ci), ("dx_channel_sum", vp)]
 
 
 class ConvtWgradArgs(C.Structure):

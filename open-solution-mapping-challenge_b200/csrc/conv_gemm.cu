@@ -318,6 +318,9 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
   }
   p.accumulate = a->accumulate;
   p.aux_mode = a->bn_z ? 2 : (a->relu_mask ? 1 : 0);
+  MCB_REQUIRE(!(a->dx_channel_sum && (!a->relu_mask || a->accumulate)),
+              "conv_dgrad: dx_channel_sum needs relu_mask and a complete (non-accumulated) gradient");
+  if (a->dx_channel_sum) p.bn_dbeta = a->dx_channel_sum;
   if (a->bn_z) {
     MCB_REQUIRE(a->bn_mean && a->bn_invstd && a->bn_gamma && a->bn_beta && a->bn_dbeta && a->bn_dgamma,
                 "conv_dgrad: incomplete bn reduction args");
@@ -411,6 +414,9 @@ extern "C" int mcb_convt_dgrad(const mcb_convt_dgrad_args* a, void* stream) {
                                  out_cw * 2)) return r;
     p.aux_mode = 1;
   }
+  MCB_REQUIRE(!(a->dx_channel_sum && (!a->relu_mask || a->accumulate)),
+              "convt_dgrad: dx_channel_sum needs relu_mask and a complete (non-accumulated) gradient");
+  p.bn_dbeta = a->dx_channel_sum;
   return launch_conv(BN, BK, true, p, (int)m_tiles, a->cin / BN, 1, st);
 }
 

@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     for (int j = 0; j < CH; ++j) racc1[j] = racc2[j] = 0.f;
     int racc_nt = -1;
     const int aux_mode = p.aux_mode;
-    const bool do_red = (p.stats != nullptr || aux_mode == 2);
+    // aux 1 with bn_dbeta set: per-channel sum of the masked gradient (bias gradient of the producing layer)
+    const bool do_red = (p.stats != nullptr || aux_mode == 2 || (aux_mode == 1 && p.bn_dbeta != nullptr));
     // aux modes use the four chunk buffers as {out[half], aux[half]}
     uint8_t* abuf = out_stage + (size_t)(2 + half) * OUT_CHUNK_BYTES;
     uint32_t aux_n = 0;
@@ -401,12 +402,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         for (int j = 0; j < CH; ++j) {
           if (j < my_chunks) {
             const int ch = p.n_off + racc_nt * BN + (ALT ? 0 : half + 2 * j) * OUT_CW + eth;
-            if (aux_mode != 2) {
+            if (aux_mode == 0) {
               atomicAdd(p.stats + ch, racc1[j]);
               atomicAdd(p.stats + p.stats_c + ch, racc2[j]);
             } else {
               atomicAdd(p.bn_dbeta + ch, racc1[j]);
-              atomicAdd(p.bn_dgamma + ch, racc2[j]);
+              if (aux_mode == 2) atomicAdd(p.bn_dgamma + ch, racc2[j]);
             }
             racc1[j] = racc2[j] = 0.f;
           }
@@ -583,6 +584,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                 if (!(hi2 != 0 && hi2 < 0x8000u)) o[e] &= 0x0000FFFFu;
               }
               *reinterpret_cast<uint4*>(cbuf + off) = make_uint4(o[0], o[1], o[2], o[3]);
+              if (do_red) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  s1[2 * e] += __uint_as_float(o[e] << 16);
+                  s1[2 * e + 1] += __uint_as_float(o[e] & 0xFFFF0000u);
+                }
+              }
             } else {
               const uint4 zk = *reinterpret_cast<const uint4*>(abuf + off);
               const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zk);

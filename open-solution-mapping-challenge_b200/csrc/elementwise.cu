@@ -63,16 +63,37 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ x, float* 
 // ------------------------------------------------------------------------------------------ stem im2col
 // 7x7 stride-2 pad-3 conv over a 3-channel fp32 NCHW image becomes a [N*Ho*Wo] x 192 bf16 matrix
 // (k = (ky*7 + kx)*3 + c for k < 147, zero beyond) consumed by the 1x1 GEMM path.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ col, int N, int H, int W) {
+constexpr int STEM_SW = 32;                      // output pixels per strip (one output row)
+constexpr int STEM_COLS = 2 * STEM_SW + 5;       // input columns a strip touches
+// One CTA = one strip of 32 output pixels of one output row: the 7 x 69 x 3 input patch is staged in shared memory
+// with coalesced loads (each input element is read from global once per strip instead of once per tap), then every
+// thread assembles 16-byte groups of 8 k-values; consecutive threads write consecutive 16-byte groups.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ col, int N,
+                                                          int H, int W) {
   mcb::pdl_prologue();
+  __shared__ float s[3][7][STEM_COLS + 1];
   const int Ho = H / 2, Wo = W / 2;
-  const long total = (long)N * Ho * Wo * 24;  // 24 groups of 8 k-values per output pixel
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int g = i % 24;
-    const long p = i / 24;
-    const int ox = p % Wo;
-    const int oy = (p / Wo) % Ho;
-    const int n = p / ((long)Wo * Ho);
+  const int strips = (Wo + STEM_SW - 1) / STEM_SW;
+  const int strip = blockIdx.x % strips;
+  const int oy = (blockIdx.x / strips) % Ho;
+  const int n = blockIdx.x / (strips * Ho);
+  const int ox0 = strip * STEM_SW;
+  const int ix0 = 2 * ox0 - 3, iy0 = 2 * oy - 3;
+  for (int e = threadIdx.x; e < 3 * 7 * STEM_COLS; e += blockDim.x) {
+    const int cc = e % STEM_COLS;
+    const int r = (e / STEM_COLS) % 7;
+    const int c = e / (STEM_COLS * 7);
+    const int iy = iy0 + r, ix = ix0 + cc;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long)n * 3 + c) * H + iy) * W + ix);
+    s[c][r][cc] = v;
+  }
+  __syncthreads();
+  const int npx = min(STEM_SW, Wo - ox0);
+  const long base = (((long)n * Ho + oy) * Wo + ox0) * 24;
+  for (int e = threadIdx.x; e < npx * 24; e += blockDim.x) {
+    const int g = e % 24;
+    const int pl = e / 24;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -80,12 +101,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict
       float v = 0.f;
       if (k < 147) {
         const int c = k % 3, kx = (k / 3) % 7, ky = k / 21;
-        const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long)n * 3 + c) * H + iy) * W + ix);
+        v = s[c][ky][2 * pl + kx];
       }
       f[j] = v;
     }
-    reinterpret_cast<uint4*>(col)[i] = pack8(f);
+    reinterpret_cast<uint4*>(col)[base + e] = pack8(f);
   }
 }
 // master stem weight fp32 [7][7][64][3] (tap-major like every conv) <-> GEMM operand bf16 [64][192]
@@ -647,8 +667,9 @@ extern "C" int mcb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int n, int c, 
 extern "C" int mcb_stem_im2col(const float* x, void* col, int n, int h, int w, void* stream) {
   MCB_REQUIRE(x && col, "null pointer");
   MCB_REQUIRE(h % 2 == 0 && w % 2 == 0, "stem_im2col: odd size");
-  const long total = (long)n * (h / 2) * (w / 2) * 24;
-  launch_pdl(stem_im2col_kernel, grid_for(total, 256), 256, 0, ST, x, (bf16*)col, n, h, w);
+  const long ctas = (long)n * (h / 2) * (((w / 2) + STEM_SW - 1) / STEM_SW);  // one per strip of an output row
+  MCB_REQUIRE(ctas < (1L << 31), "stem_im2col: too many strips");
+  launch_pdl(stem_im2col_kernel, dim3((unsigned)ctas), 256, 0, ST, x, (bf16*)col, n, h, w);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

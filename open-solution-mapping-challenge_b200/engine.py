@@ -70,6 +70,8 @@ class Plan:
         self._stats_used = 0
         self.graph_fwd = self.graph_bwd = None
         self._side = None
+        self.bias_sum = {}         # id(conv+bias+ReLU output) -> its bias-gradient vector (fused into the consumer's dgrad)
+        self.bias_fused = set()
         self.x_in = torch.zeros((n, 3, h, w), dtype=F32, device=self.dev)
         self.dlogits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
         self.logits = torch.zeros((n, net.num_classes, h, w), dtype=F32, device=self.dev)
@@ -191,13 +193,17 @@ class Plan:
         cin = x.shape[3]
         if acc and relu_mask is not None:
             raise RuntimeError("plan error: masked dgrad cannot accumulate")
+        csum = None
+        if relu_mask is x and id(x) in self.bias_sum:
+            csum = self.bias_sum[id(x)]      # x = relu(conv(.) + b): its bias gradient is the channel sum of grad(x)
+            self.bias_fused.add(id(x))
         red = None
         if bn_reduce is not None:
             zz, bb = bn_reduce
             red = (zz, bb.mean, bb.invstd, bb.gamma, bb.beta, bb.dbeta, bb.dgamma)
             relu_mask = None  # recomputed from z in the epilogue
         B.add("conv_dgrad", lambda: ops.conv_dgrad(dz, w16, k, s, hw, cin=cin, ci_off=ci_off, relu_mask=relu_mask,
-                                                   accumulate=acc, out=gx, bn_reduce=red),
+                                                   accumulate=acc, out=gx, bn_reduce=red, channel_sum=csum),
               2.0 * dz.numel() * cin * k * k,
               _nb(dz, gx, relu_mask) + (_nb(gx) if acc else 0) + 2.0 * k * k * dz.shape[3] * cin,
               "%d<-%d k%d s%d @%dx%dx%d%s" % (cin, dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2],
@@ -376,6 +382,8 @@ class Plan:
         mid = self.act(n, h, w, cmid)
         out = self.act(n, 2 * h, 2 * w, cout)
         ctot = c1 + (skip.shape[3] if skip is not None else 0)
+        if self.training:
+            self.bias_sum[id(out)] = net._vec(deconv.bias, net._g32)
         fc = 2.0 * mid.numel() * ctot * 9
         ft = 2.0 * mid.numel() * cout * 16
         F.add("conv_fwd", lambda: ops.conv_fwd(x1, w16, 3, 1, bias=b1, relu=True, x2=skip, out=mid), fc,
@@ -390,12 +398,12 @@ class Plan:
                 gb2 = net._vec(deconv.bias, net._g32)
                 gw = net._packed(conv.weight, net._g32)
                 gb1 = net._vec(conv.bias, net._g32)
-                B.add("channel_sum", lambda: ops.channel_sum(g_out, gb2), 0, _nb(g_out))
+                if id(out) not in self.bias_fused:   # else: summed in the epilogue of the dgrad that produced g_out
+                    B.add("channel_sum", lambda: ops.channel_sum(g_out, gb2), 0, _nb(g_out))
                 dd = "%d->%d @%dx%dx%d" % (cmid, cout, n, h, w)
                 B.add("convt_wgrad", lambda: ops.convt_wgrad(g_out, mid, gwt), ft, _nb(g_out, mid, gwt), dd)
-                B.add("convt_dgrad", lambda: ops.convt_dgrad(g_out, wt16, relu_mask=mid, out=g_mid), ft,
+                B.add("convt_dgrad", lambda: ops.convt_dgrad(g_out, wt16, relu_mask=mid, out=g_mid, channel_sum=gb1), ft,
                       _nb(g_out, wt16, mid, g_mid), dd)
-                B.add("channel_sum", lambda: ops.channel_sum(g_mid, gb1), 0, _nb(g_mid))
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(g_mid, x1, gw, 3, 1, ci_off=0),
                       2.0 * mid.numel() * c1 * 9, _nb(g_mid, x1), "dec %d->%d k3 @%dx%dx%d" % (c1, cmid, n, h, w))
                 if skip is not None:

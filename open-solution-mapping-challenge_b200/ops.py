@@ -64,7 +64,7 @@ def conv_fwd(x, w, ksize, stride=1, bias=None, relu=False, stats=None, x2=None, 
 
 
 def conv_dgrad(dy, w, ksize, stride, in_hw, cin=None, ci_off=0, relu_mask=None, accumulate=False, out=None,
-               bn_reduce=None):
+               bn_reduce=None, channel_sum=None):
     """bn_reduce = (z, mean, invstd, gamma, beta, dbeta, dgamma): fuse the backward of the conv-BN-ReLU unit that
     produced this conv's input into the epilogue (ReLU mask recomputed from z, BatchNorm-backward reductions);
     relu_mask must then be None"""
@@ -88,6 +88,8 @@ def conv_dgrad(dy, w, ksize, stride, in_hw, cin=None, ci_off=0, relu_mask=None, 
         a.bn_z = _chk(z).data_ptr(); a.bn_mean = mean.data_ptr(); a.bn_invstd = invstd.data_ptr()
         a.bn_gamma = gamma.data_ptr(); a.bn_beta = beta.data_ptr()
         a.bn_dbeta = dbeta.data_ptr(); a.bn_dgamma = dgamma.data_ptr()
+    if channel_sum is not None:
+        a.dx_channel_sum = _chk(channel_sum, torch.float32).data_ptr()
     L.call("mcb_conv_dgrad", a)
     return out
 
@@ -120,7 +122,7 @@ def convt_fwd(x, w, bias=None, relu=False, out=None):
     return out
 
 
-def convt_dgrad(dy, w, relu_mask=None, accumulate=False, out=None):
+def convt_dgrad(dy, w, relu_mask=None, accumulate=False, out=None, channel_sum=None):
     _chk(dy); _chk(w)
     n, h2, w2, cout = dy.shape
     h, wd = h2 // 2, w2 // 2
@@ -133,6 +135,8 @@ def convt_dgrad(dy, w, relu_mask=None, accumulate=False, out=None):
     a.weight = w.data_ptr(); a.cout = cout; a.dx = _chk(out).data_ptr()
     a.relu_mask = _chk(relu_mask).data_ptr() if relu_mask is not None else None
     a.accumulate = int(accumulate)
+    if channel_sum is not None:
+        a.dx_channel_sum = _chk(channel_sum, torch.float32).data_ptr()
     L.call("mcb_convt_dgrad", a)
     return out
 

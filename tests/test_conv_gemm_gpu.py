@@ -125,8 +125,11 @@ def test_conv_dgrad(mcb, cuda, n, h, w, cin, cout, k, stride):
     assert_close_bf16(nchw(dx), ref, "conv_dgrad")
     # relu mask
     act = bf16r(torch.randn(n, cin, h, w, generator=g))
-    dx2 = ops.conv_dgrad(dyd, wp, k, stride, (h, w), relu_mask=nhwc(act).to(cuda, torch.bfloat16))
+    csum = torch.zeros(cin, device=cuda)
+    dx2 = ops.conv_dgrad(dyd, wp, k, stride, (h, w), relu_mask=nhwc(act).to(cuda, torch.bfloat16), channel_sum=csum)
     assert_close_bf16(nchw(dx2), ref * (act > 0).float(), "conv_dgrad mask")
+    # fused bias gradient of the producing layer = per-channel sum of the STORED masked gradient
+    assert torch.allclose(csum.cpu(), nchw(dx2).float().cpu().sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
     # accumulate on top of an existing gradient
     base = bf16r(torch.randn(n, cin, h, w, generator=g))
     acc = nhwc(base).to(cuda, torch.bfloat16)
@@ -224,6 +227,11 @@ def test_convt(mcb, cuda, n, h, w, cin, cout):
     dyd = nhwc(dy).to(cuda, torch.bfloat16)
     dx = ops.convt_dgrad(dyd, wp)
     assert_close_bf16(nchw(dx), xr.grad, "convt_dgrad")
+    act = bf16r(torch.randn(*xr.shape, generator=g))
+    csum = torch.zeros(xr.shape[1], device=cuda)
+    dxm = ops.convt_dgrad(dyd, wp, relu_mask=nhwc(act).to(cuda, torch.bfloat16), channel_sum=csum)
+    assert_close_bf16(nchw(dxm), xr.grad * (act > 0).float(), "convt_dgrad mask")
+    assert torch.allclose(csum.cpu(), nchw(dxm).float().cpu().sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
     dw = torch.zeros(16, cout, cin, device=cuda)
     ops.convt_wgrad(dyd, xd, dw)
     got = ops.unpack_convt_weight(dw).cpu()
