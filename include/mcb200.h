@@ -193,6 +193,10 @@ int mcb_final_conv_bwd(const void* x, const float* w, const float* dlogits, void
 /* torch.optim.Adam with L2 (src/models.py:57,287-292) over one flat fp32 arena; refreshes the bf16 operand copy */
 int mcb_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, long n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* same update with the step-dependent scalars read from DEVICE memory: hyper = {lr, 1-beta1^t, sqrt(1-beta2^t)}
+   (fp32[3]), so the launch can be captured once into a CUDA graph and replayed every step */
+int mcb_adam_step_dyn(float* p, const float* g, float* m, float* v, void* p_bf16, long n, const float* hyper,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 int mcb_cast_f32_bf16(const float* x, void* y, long n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------

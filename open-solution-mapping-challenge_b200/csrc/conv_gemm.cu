@@ -89,8 +89,14 @@ static int launch_conv(int BN, int BK, bool b_mn, ConvGemmParams& p, int m_tiles
 }
 
 // haloed 3x3 path: worth it when 8x16 single-image tiles cover the image without much waste
-static bool use_halo(int ksize, int stride, int W, int H) {
-  if (ksize != 3 || stride != 1 || env_int("MCB_HALO", 0) == 0) return false;
+// k_channels = channels per tap of the GEMM-K dimension.  Sweep (gpurun r1, tools/sweep_gemm.py): the haloed tile wins
+// ~9% where the nine per-tap fetches made the kernel L2-bound (>= 128 channels on large images whose extent the 8x16
+// tile divides), and loses on thin layers (the per-tile issue cost dominates) and on ragged small images.
+// MCB_HALO: 0 never, 1 whenever the tile covers >= 80% (old behaviour), 2 (default) the measured-win rule.
+static bool use_halo(int ksize, int stride, int W, int H, int k_channels) {
+  const int mode = env_int("MCB_HALO", 2);
+  if (ksize != 3 || stride != 1 || mode == 0) return false;
+  if (mode == 2) return k_channels >= env_int("MCB_HALO_MINC", 128) && W % 8 == 0 && H % 16 == 0 && W >= 80;
   const double eff = (double)W * H / ((double)((W + 7) / 8) * 8 * ((H + 15) / 16) * 16);
   return eff >= 0.8;
 }
@@ -178,7 +184,7 @@ extern "C" int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream) {
 
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  const bool halo = use_halo(a->ksize, a->stride, Wo, Ho);
+  const bool halo = use_halo(a->ksize, a->stride, Wo, Ho, nsrc == 2 ? std::min(a->cin[0], a->cin[1]) : a->cin[0]);
   if (halo) { p.bw = 8; p.bh = 16; p.bn = 1; }
   else pick_tile(Wo, Ho, N, 128, 1, &p.bw, &p.bh, &p.bn);
   p.rows = p.bw * p.bh * p.bn;
@@ -249,7 +255,7 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   const int Wv = (a->stride == 1) ? W : W / 2, Hv = (a->stride == 1) ? H : H / 2;
-  const bool halo = use_halo(a->ksize, a->stride, Wv, Hv);
+  const bool halo = use_halo(a->ksize, a->stride, Wv, Hv, a->cout);
   if (halo) { p.bw = 8; p.bh = 16; p.bn = 1; }
   else pick_tile(Wv, Hv, N, 128, 1, &p.bw, &p.bh, &p.bn);
   p.rows = p.bw * p.bh * p.bn;

@@ -89,8 +89,11 @@ struct WgradParams {
   int a_chunks;  // chunks actually loaded (1 or 2); missing ones alias chunk 0 (LBO = 0)
 };
 
+// (pointer + offset, not an integer round trip: the result provably stays in the shared window, so every access below
+// compiles to LDS/STS with 32-bit addressing instead of generic LD/ST with 64-bit address arithmetic)
 __device__ __forceinline__ uint8_t* align_up_1024(uint8_t* p) {
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  return p + ((1024u - (a & 1023u)) & 1023u);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -424,6 +427,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const int ncol0 = nt * BN;
       const int ox = x0 + wi, oy = y0 + hi, on = n0 + ni;
       const bool valid = row < p.rows && ox < p.Wv && oy < p.Hv && on < p.Nimg;
+      // every row of the tile is a real output pixel (the common case): the second pass skips the per-row checks
+      const bool tile_full = p.rows == 128 && x0 + p.bw <= p.Wv && y0 + p.bh <= p.Hv && n0 + p.bn <= p.Nimg;
       const int acc = it & 1;
       if (ALT && acc != half) {
         // not this half's tile: only keep the accumulator hand-off in lock-step (8 arrivals per tile)
@@ -456,26 +461,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         const int chunk = ALT ? 0 : half + 2 * cj;
         uint8_t* cbuf = aux_mode != 0 ? out_stage + (size_t)half * OUT_CHUNK_BYTES
                                       : out_stage + (size_t)((it % OUT_BUFS) * OUT_CHUNKS + chunk) * OUT_CHUNK_BYTES;
-        // the store that used this buffer OUT_BUFS tiles ago must have finished reading it (bulk groups retire in
-        // order; this thread commits CH groups per tile)
-        if (eth == 0) {
-          // (ALT: this half stores every other tile, so OUT_BUFS tiles ago = OUT_BUFS / 2 of its own groups)
-          constexpr int PENDING_OK = ALT ? OUT_BUFS / 2 - 1 : OUT_BUFS * CH - 1;
-          if (aux_mode != 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // single out buffer
-          else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING_OK) : "memory");
-        }
+        // Staging-buffer reuse.  Plain / statistics mode: this half rotates over two buffers, and the wait for the
+        // buffer of the NEXT chunk sits just before this chunk's hand-off barrier below (one barrier less per chunk).
+        // Aux modes have a single output buffer per half: wait for its previous store here.
         if (cj == 0) my_row_pix[row] = pix;
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (aux_mode != 0) {
+          if (eth == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
 
+        // all TMEM loads of the chunk are in flight before the first one is consumed
+        uint32_t vv[OUT_CW / 32][32];
+#pragma unroll
+        for (int sub = 0; sub < OUT_CW / 32; ++sub) tc::tmem_ld_32x32(tmem_acc + (uint32_t)(chunk * OUT_CW + sub * 32), vv[sub]);
+        tc::tmem_ld_wait();
 #pragma unroll
         for (int sub = 0; sub < OUT_CW / 32; ++sub) {
           const int c0 = chunk * OUT_CW + sub * 32;
-          uint32_t v[32];
-          tc::tmem_ld_32x32(tmem_acc + (uint32_t)c0, v);
-          tc::tmem_ld_wait();
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(vv[sub][i]);
           if (p.scale != nullptr) {
             const float4* sp = reinterpret_cast<const float4*>(p.scale + p.n_off + ncol0 + c0);
 #pragma unroll
@@ -530,6 +535,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);
         }
         tc::fence_proxy_async_smem();
+        // (all previous stores of this thread retired their smem reads -> the other rotating buffer is free for the
+        // next chunk; the newest of them was issued a whole chunk ago, so this does not stall in practice)
+        if (aux_mode == 0 && eth == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 
         if (do_red || aux_mode != 0) {
@@ -547,22 +555,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const int ch0 = p.n_off + ncol0 + chunk * OUT_CW + cg * 8;
           float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s1[j] = s2[j] = 0.f;
-            mu[j] = bnred ? __ldg(p.bn_mean + ch0 + j) : 0.f;
-            is[j] = bnred ? __ldg(p.bn_invstd + ch0 + j) : 0.f;
-            sc[j] = bnred ? __ldg(p.bn_gamma + ch0 + j) * is[j] : 0.f;       // same expressions as the forward's
-            sh[j] = bnred ? __ldg(p.bn_beta + ch0 + j) - mu[j] * sc[j] : 0.f;  // bn_train_coef (elementwise.cu)
+          for (int j = 0; j < 8; ++j) s1[j] = s2[j] = mu[j] = is[j] = sc[j] = sh[j] = 0.f;
+          if (bnred) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              mu[j] = __ldg(p.bn_mean + ch0 + j);
+              is[j] = __ldg(p.bn_invstd + ch0 + j);
+              sc[j] = __ldg(p.bn_gamma + ch0 + j) * is[j];       // same expressions as the forward's
+              sh[j] = __ldg(p.bn_beta + ch0 + j) - mu[j] * sc[j];  // bn_train_coef (elementwise.cu)
+            }
           }
+          // rows rg*ROWSc .. +ROWSc-1; the swizzle term of row r depends only on rr (OUT_CW 64: r & 7 == rr; 32:
+          // (r >> 1) & 3 == ((rg & 1) * 2 + (rr >> 1))), so every offset is base + compile-time pieces
+          const uint32_t row0_off = (uint32_t)(rg * ROWSc) * OUT_ROW_BYTES;
+          const int swz_rg = (OUT_CW == 64) ? 0 : (rg & 1) * 2;
 #pragma unroll
           for (int rr = 0; rr < ROWSc; ++rr) {
-            const int r = rg * ROWSc + rr;
-            const int rp = my_row_pix[r];
-            if (rp < 0) continue;
-            int unit = cg;
-            if (OUT_CW == 64) unit ^= (r & 7);
-            else unit ^= ((r >> 1) & 3);
-            const size_t off = (size_t)r * OUT_ROW_BYTES + unit * 16;
+            if (!tile_full && my_row_pix[rg * ROWSc + rr] < 0) continue;   // ragged tiles only
+            const int unit = (OUT_CW == 64) ? (cg ^ rr) : (cg ^ (swz_rg + (rr >> 1)));
+            const uint32_t off = row0_off + (uint32_t)rr * OUT_ROW_BYTES + (uint32_t)unit * 16;
             const uint4 pk = *reinterpret_cast<const uint4*>(cbuf + off);
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
             if (aux_mode == 0) {

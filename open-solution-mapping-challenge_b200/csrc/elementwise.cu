@@ -622,10 +622,17 @@ __global__ void final_conv_bwd_kernel(const uint4* __restrict__ x, const float* 
 // ------------------------------------------------------------------------------------------ fused Adam
 // torch.optim.Adam with L2 weight decay folded into the gradient (src/models.py:57,287-292), over one flat fp32
 // parameter arena; also refreshes the bf16 operand copy of the weights (same layout) for the next forward.
+// hyper (optional, device): {lr, bc1, sqrt(bc2)} of this step -- lets the launch sit inside a replayed CUDA graph
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, bf16* __restrict__ p_bf16, long n, float lr, float beta1,
-                            float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+                            float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
+                            const float* __restrict__ hyper) {
   mcb::pdl_prologue();
+  if (hyper != nullptr) {
+    lr = __ldg(hyper);
+    bc1 = __ldg(hyper + 1);
+    bc2_sqrt = __ldg(hyper + 2);
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float pi = p[i];
     const float gi = g[i] * grad_scale + wd * pi;
@@ -856,7 +863,17 @@ extern "C" int mcb_adam_step(float* p, const float* g, float* m, float* v, void*
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   launch_pdl(adam_kernel, grid_for(n, 256), 256, 0, ST, p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay,
-                                                (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                (float)bc1, (float)sqrt(bc2), grad_scale, (const float*)nullptr);
+  MCB_LAUNCH_CHECK();
+  return MCB_OK;
+}
+extern "C" int mcb_adam_step_dyn(float* p, const float* g, float* m, float* v, void* p_bf16, long n,
+                                 const float* hyper, float beta1, float beta2, float eps, float weight_decay,
+                                 float grad_scale, void* stream) {
+  MCB_REQUIRE(p && g && m && v && hyper, "adam_dyn: null pointer");
+  if (n == 0) return MCB_OK;
+  launch_pdl(adam_kernel, grid_for(n, 256), 256, 0, ST, p, g, m, v, (bf16*)p_bf16, n, 0.f, beta1, beta2, eps,
+             weight_decay, 1.f, 1.f, grad_scale, hyper);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

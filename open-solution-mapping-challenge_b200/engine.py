@@ -436,9 +436,11 @@ class Plan:
         for op in self.fwd_ops:
             op()
 
-    def _run_bwd(self, first=0, last=None):
+    def _run_bwd(self, first=0, last=None, hooks=None):
         """backward layers [first, last) in execution (reverse-forward) order; the gradient arena is zeroed with the
-        first layer"""
+        first layer.  hooks = {layer_index: fn}: fn() runs ON THE SIDE STREAM once every launch of the layers before
+        `layer_index` (main chain and weight-gradient GEMMs) is ordered before it -- used for per-segment optimizer
+        updates that overlap the rest of the backward pass."""
         if first == 0:
             self.net._g32.zero_()
         # Weight/bias-gradient launches are leaves of the backward graph (they only add into the gradient arena): they
@@ -466,7 +468,23 @@ class Plan:
             pending.clear()
             forked = True
 
-        for layer in self.bwd_layers[first:last]:
+        def run_hook(idx):
+            nonlocal forked
+            if hooks and idx in hooks:
+                if not use_side:
+                    hooks[idx]()
+                    return
+                flush()
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._side.wait_event(ev)
+                with torch.cuda.stream(self._side):
+                    hooks[idx]()
+                forked = True
+
+        n_layers = len(self.bwd_layers) if last is None else last
+        for li, layer in enumerate(self.bwd_layers[first:last], start=first):
+            run_hook(li)
             for op in layer:
                 if use_side and op.kind in _SIDE_KINDS and op.desc:
                     pending.append(op)
@@ -479,6 +497,7 @@ class Plan:
                     if op.kind in ("conv_dgrad", "convt_dgrad"):
                         flush()
         flush()
+        run_hook(n_layers)
         if forked:
             ev = torch.cuda.Event()
             ev.record(self._side)

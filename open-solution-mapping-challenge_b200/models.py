@@ -367,6 +367,14 @@ class FusedTrainStep:
         if self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "1":
             self.segments = self.plan.bwd_segments()
             self._comm_stream = torch.cuda.Stream(device=dev)
+        # single GPU: the Adam update of a finished arena segment (decoder | layer4 | rest) rides on the backward's side
+        # stream, inside the graph, overlapping the data-gradient GEMMs of the layers below (HBM-bound next to
+        # tensor-bound).  Its step-dependent scalars live in a 3-float device tensor refreshed before every replay.
+        self.adam_in_graph = self.world == 1 and os.environ.get("MCB_ADAM_SIDE", "1") == "1"
+        self._hyper = torch.zeros(3, dtype=torch.float32, device=dev)
+        # pinned staging ring: a slot is rewritten only after the copy that last read it has executed
+        self._hyper_ring = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+        self._adam_cfg = None
 
     # segments ----------------------------------------------------------------------------------------------------
     def _seg_forward(self):
@@ -384,7 +392,16 @@ class FusedTrainStep:
             ops.loss_grad(self.plan.logits, self.target, self.sums, self.plan.dlogits, self.loss,
                           global_pixels=self.pixels * self.world, mode=self.loss_mode, **self.loss_cfg)
         if seg is None:
-            self.plan._run_bwd()
+            hooks = None
+            if self.adam_in_graph:
+                net = self.net
+                betas, eps, wd = self._adam_cfg
+
+                def upd(lo, hi):
+                    return lambda: ops.adam_step_dyn(net._p32[lo:hi], net._g32[lo:hi], self.m[lo:hi], self.v[lo:hi],
+                                                     net._w16[lo:hi], self._hyper, betas, eps, wd, 1.0)
+                hooks = {last: upd(lo, hi) for _, last, lo, hi in self.plan.bwd_segments()}
+            self.plan._run_bwd(hooks=hooks)
         else:
             self.plan._run_bwd(seg[0], seg[1])
 
@@ -442,6 +459,19 @@ class FusedTrainStep:
     def step(self, X, target, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         finish_target = self._stage_inputs(X, target)
         self.t += 1
+        if self.adam_in_graph:
+            cfg = (tuple(betas), eps, weight_decay)
+            if self._adam_cfg is None:
+                self._adam_cfg = cfg
+            elif self._adam_cfg != cfg:   # baked into the captured launches
+                raise RuntimeError("Adam betas / eps / weight_decay changed after the train step was captured")
+            host, ev = self._hyper_ring[self.t % len(self._hyper_ring)]
+            ev.synchronize()
+            host[0] = lr
+            host[1] = 1.0 - betas[0] ** self.t
+            host[2] = (1.0 - betas[1] ** self.t) ** 0.5
+            self._hyper.copy_(host, non_blocking=True)
+            ev.record()
         first = self.graphs is None and self.use_graphs
         if first or not self.use_graphs:
             self._seg_forward()
@@ -477,7 +507,8 @@ class FusedTrainStep:
                     works.append(dist.all_reduce(grad_slice, async_op=True))
             for wk in works:
                 wk.wait()
-        self._adam(lr, betas, eps, weight_decay)
+        if not self.adam_in_graph:
+            self._adam(lr, betas, eps, weight_decay)
         if first:
             torch.cuda.synchronize()
             self._capture()
@@ -485,4 +516,4 @@ class FusedTrainStep:
 
     def count_launches(self):
         """kernel launches of one step (our kernels + memsets issued by the plan)"""
-        return self.plan.launches_fwd + self.plan.launches_bwd + 4
+        return self.plan.launches_fwd + self.plan.launches_bwd + (6 if self.adam_in_graph else 4)

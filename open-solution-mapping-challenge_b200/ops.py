@@ -283,6 +283,12 @@ def adam_step(p, g, m, v, p_bf16, step, lr, betas=(0.9, 0.999), eps=1e-8, weight
             betas[0], betas[1], eps, weight_decay, int(step), grad_scale)
 
 
+def adam_step_dyn(p, g, m, v, p_bf16, hyper, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """Adam over a (slice of the) flat arena with {lr, 1-b1^t, sqrt(1-b2^t)} read from the device tensor `hyper`"""
+    L.fcall("mcb_adam_step_dyn", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), L.dp(p_bf16), p.numel(),
+            hyper.data_ptr(), betas[0], betas[1], eps, weight_decay, grad_scale)
+
+
 def cast_bf16(x, out):
     L.fcall("mcb_cast_f32_bf16", _chk(x, F32).data_ptr(), _chk(out).data_ptr(), x.numel())
     return out

@@ -87,6 +87,34 @@ def test_conv_fwd_integer_exact(mcb, cuda):
     assert torch.equal(nchw(y).float().cpu(), ref)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 16, 64, 128), (1, 32, 24, 128, 64), (1, 16, 16, 32, 32),
+                                             (2, 20, 20, 64, 64)])
+def test_conv3x3_haloed_tile_path(mcb, cuda, monkeypatch, n, h, w, cin, cout):
+    """MCB_HALO=1 forces the haloed-tile 3x3 path (one TMA box per channel chunk serves the nine taps through
+    row-shifted UMMA descriptors; default rule: >= 128 channels on large images): forward (+stats, integer-exact),
+    plain / masked data gradient, against the same references as the per-tap path"""
+    from mcb200 import ops
+    monkeypatch.setenv("MCB_HALO", "1")
+    g = torch.Generator().manual_seed(11 + h + cin)
+    x = torch.randint(-1, 2, (n, cin, h, w), generator=g).float()
+    wt = (torch.rand(cout, cin, 3, 3, generator=g) < 0.1).float() * torch.randint(-1, 2, (cout, cin, 3, 3), generator=g)
+    ref = F.conv2d(x, wt, None, padding=1)
+    stats = torch.zeros(2 * cout, device=cuda)
+    wp = ops.pack_conv_weight(wt).to(cuda, torch.bfloat16)
+    y = ops.conv_fwd(nhwc(x).to(cuda, torch.bfloat16), wp, 3, stats=stats)
+    assert torch.equal(nchw(y).float().cpu(), ref)
+    assert torch.allclose(stats[:cout].cpu(), ref.sum(dim=(0, 2, 3)), atol=1e-2)
+    dy = bf16r(torch.randn(n, cout, h, w, generator=g))
+    wr = bf16r(torch.randn(cout, cin, 3, 3, generator=g) / (cout * 9) ** 0.5)
+    dref = torch.nn.grad.conv2d_input((n, cin, h, w), wr, dy, padding=1)
+    wrp = ops.pack_conv_weight(wr).to(cuda, torch.bfloat16)
+    dyd = nhwc(dy).to(cuda, torch.bfloat16)
+    assert_close_bf16(nchw(ops.conv_dgrad(dyd, wrp, 3, 1, (h, w))), dref, "halo dgrad")
+    act = bf16r(torch.randn(n, cin, h, w, generator=g))
+    dxm = ops.conv_dgrad(dyd, wrp, 3, 1, (h, w), relu_mask=nhwc(act).to(cuda, torch.bfloat16))
+    assert_close_bf16(nchw(dxm), dref * (act > 0).float(), "halo dgrad mask")
+
+
 def test_conv_fwd_concat(mcb, cuda):
     from mcb200 import ops
     g = torch.Generator().manual_seed(3)
