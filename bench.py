@@ -358,6 +358,16 @@ def main():
                      "what": "conv/convT fwd+dgrad+wgrad tcgen05 GEMM family: algorithmic conv FLOPs of the step "
                              "(%.2f GFLOP/tile) / whole-step time per GPU" % (fpt / 1e9)},
     }
+    # DRAM traffic of the GEMM family over one step, from the committed ncu capture of this same workload (a number
+    # taken under the profiler is evidence, not a bench value): compare with the family's algorithmic bytes
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_gemm_traffic.json")
+    if (args.encoder, args.batch, args.size) == (101, 32, 320) and os.path.exists(tj):
+        with open(tj) as f:
+            tr = json.load(f)
+        line["roofline"]["traffic"] = int(tr["dram_bytes"])
+        line["roofline"]["traffic_unit"] = "DRAM bytes per step per GPU, summed over the family's %d launches " \
+                                           "(ncu dram__bytes_read.sum + dram__bytes_write.sum, cold-cache replay)" % tr["launches"]
+        line["roofline"]["traffic_source"] = "profiles/r01c_gemm_traffic.json"
     if not args.no_breakdown:
         bd, total = breakdown(fused)
         note("breakdown done")
@@ -368,6 +378,7 @@ def main():
         line["roofline"]["gemm_family_ms"] = round(gemm_ms, 3)
         line["roofline"]["gemm_family_tflops"] = round(gemm_fl / gemm_ms, 1) if gemm_ms else None
         line["roofline"]["gemm_family_share_of_step"] = round(gemm_ms / total, 4)
+        line["roofline"]["gemm_family_algorithmic_bytes"] = int(sum((v["algo_gbs"] or 0) * v["ms"] * 1e6 for v in gemm))
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_arm(args, sample_batch=2, steps=2, warmup=1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -29,17 +29,18 @@ plan = net.plan(batch, size, size, True) if False else None
 plan = net.plan(1, size, size, True)
 ops = list(plan.fwd_ops) + [o for l in plan.bwd_layers for o in l]
 out = []
-i = 0
+# one queue per kernel: the weight-gradient GEMMs run on a side stream (launched later than their place in the plan), but
+# the launches of ONE kernel keep their plan order
+queues = {want: [r for r in rows if want in r[0]] for want in set(KERNEL.values())}
+ptr = {want: 0 for want in queues}
 for o in ops:
     want = KERNEL.get(o.kind)
     if want is None:
         continue
-    while i < len(rows) and want not in rows[i][0]:
-        i += 1
-    if i >= len(rows):
-        break
-    name, grid, ns = rows[i]
-    i += 1
+    if ptr[want] >= len(queues[want]):
+        continue
+    name, grid, ns = queues[want][ptr[want]]
+    ptr[want] += 1
     m = re.search(r"(conv_gemm_kernel|wgrad_kernel)(<[^>]*>)", name)
     out.append((ns, o.kind, o.desc.replace("@1x", "@%dx" % batch), (m.group(2) if m else ""), grid, o.flops * batch, o.bytes * batch))
 tot = sum(r[0] for r in out)
