@@ -307,39 +307,41 @@ __global__ void score_finalize_kernel(const double* __restrict__ sums, const int
   scores[i] = c > 0 ? (sums[i] / (double)c) * sqrt((double)c) : nan("");
 }
 
-// build_score with one CTA per plane and no host round trip: every thread walks a CONTIGUOUS pixel range and keeps a
-// running (label, sum, count); it flushes with one native fp64 global atomic only when the label changes (a few times
-// per thread, since instances are blobs), so there is no same-address atomic storm.  Scores are written at a fixed
-// stride `kcap` per plane.  counts[plane] = number of labels of the plane (from the labelling step).
+// build_score without a host round trip, scores at a fixed stride `kcap` per plane; counts[plane] = number of labels of
+// the plane (from the labelling step).  Grid (S, planes): CTA (s, plane) owns a contiguous pixel span, every thread
+// walks a CONTIGUOUS sub-range keeping a running (label, sum, count) and flushes with one native fp64 global atomic
+// only when the label changes (a few times per thread, since instances are blobs) -- no same-address atomic storm and
+// ~8 CTAs per SM in flight instead of one CTA per plane.  The accumulators are zeroed by the caller (memset) and
+// turned into scores by score_finalize_strided_kernel.
 template <typename T>
-__global__ void __launch_bounds__(1024) score_plane_kernel(const int* __restrict__ labels, const T* __restrict__ prob,
-                                                          const int* __restrict__ counts, double* __restrict__ scores,
-                                                          double* __restrict__ gsum, int* __restrict__ gcnt, long hw,
-                                                          int kcap) {
-  const int plane = blockIdx.x;
-  const int K = min(counts[plane], kcap);
+__global__ void __launch_bounds__(256) score_runs_kernel(const int* __restrict__ labels, const T* __restrict__ prob,
+                                                         double* __restrict__ gsum, int* __restrict__ gcnt, long hw,
+                                                         int kcap, int chunk) {
+  const int plane = blockIdx.y;
   double* ps = gsum + (long)plane * kcap;
   int* pc = gcnt + (long)plane * kcap;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) { ps[i] = 0.0; pc[i] = 0; }
-  __syncthreads();
   const long base = (long)plane * hw;
-  const long chunk = (hw + blockDim.x - 1) / blockDim.x;
-  const long b = threadIdx.x * chunk, e = min(hw, b + chunk);
+  const long b = ((long)blockIdx.x * blockDim.x + threadIdx.x) * chunk;
+  const long e = min(hw, b + chunk);
   int cur = 0, cnt = 0;
   double sum = 0.0;
   for (long i = b; i < e; ++i) {
-    const int l = labels[base + i];
+    const int l = __ldg(labels + base + i);
     if (l != cur) {
       if (cur > 0 && cur <= kcap) { atomicAdd(&ps[cur - 1], sum); atomicAdd(&pc[cur - 1], cnt); }
       cur = l; cnt = 0; sum = 0.0;
     }
-    if (l > 0) { sum += (double)prob[base + i]; ++cnt; }
+    if (l > 0) { sum += (double)__ldg(prob + base + i); ++cnt; }
   }
   if (cur > 0 && cur <= kcap) { atomicAdd(&ps[cur - 1], sum); atomicAdd(&pc[cur - 1], cnt); }
-  __syncthreads();
+}
+__global__ void score_finalize_strided_kernel(const double* __restrict__ gsum, const int* __restrict__ gcnt,
+                                              const int* __restrict__ counts, double* __restrict__ scores, int kcap) {
+  const int plane = blockIdx.x;
+  const int K = min(counts[plane], kcap);
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    const int c = __ldcg(&pc[i]);  // the atomics landed in L2: read around L1
-    const double sm = __ldcg(&ps[i]);
+    const int c = gcnt[(long)plane * kcap + i];
+    const double sm = gsum[(long)plane * kcap + i];
     scores[(long)plane * kcap + i] = c > 0 ? (sm / (double)c) * sqrt((double)c) : nan("");
   }
 }
@@ -447,10 +449,18 @@ extern "C" int mcb_instance_scores_strided(const int* labels, const void* prob, 
   MCB_REQUIRE(labels && prob && counts && scores && gsum_ws && gcnt_ws, "scores_strided: null pointer");
   MCB_REQUIRE(kcap >= 1, "scores_strided: kcap %d", kcap);
   const long hw = (long)h * w;
+  MCB_CHECK_CUDA(cudaMemsetAsync(gsum_ws, 0, (size_t)planes * kcap * sizeof(double), ST));
+  MCB_CHECK_CUDA(cudaMemsetAsync(gcnt_ws, 0, (size_t)planes * kcap * sizeof(int), ST));
+  const int S = (int)std::max(1L, std::min(64L, (long)num_sms() * 8L / std::max(planes, 1)));
+  const int chunk = (int)(((hw + (long)S * 256 - 1) / ((long)S * 256) + 3) / 4 * 4);  // pixels per thread
+  const int ctas = (int)((hw + (long)chunk * 256 - 1) / ((long)chunk * 256));
+  dim3 grid(ctas, planes);
   if (prob_is_f64)
-    score_plane_kernel<double><<<planes, 1024, 0, ST>>>(labels, (const double*)prob, counts, scores, gsum_ws, gcnt_ws, hw, kcap);
+    score_runs_kernel<double><<<grid, 256, 0, ST>>>(labels, (const double*)prob, gsum_ws, gcnt_ws, hw, kcap, chunk);
   else
-    score_plane_kernel<float><<<planes, 1024, 0, ST>>>(labels, (const float*)prob, counts, scores, gsum_ws, gcnt_ws, hw, kcap);
+    score_runs_kernel<float><<<grid, 256, 0, ST>>>(labels, (const float*)prob, gsum_ws, gcnt_ws, hw, kcap, chunk);
+  MCB_LAUNCH_CHECK();
+  score_finalize_strided_kernel<<<planes, 256, 0, ST>>>(gsum_ws, gcnt_ws, counts, scores, kcap);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

@@ -57,14 +57,20 @@ def resize_batch(probs, target_size):
     return out
 
 
+_THRESHOLD_CONSTS = {}
+
+
 def threshold_batch(probs, category_layers=None):
     """probs (N, C, H, W) float32|float64 cuda -> (N, L, H, W) uint8 (0/1)"""
     assert probs.is_cuda and probs.is_contiguous() and probs.dtype in (torch.float32, torch.float64)
     n, c, h, w = probs.shape
     thr, chan = layer_thresholds(category_layers)
     assert len(category_layers or CATEGORY_LAYERS) <= c or max(chan) < c
-    t = torch.tensor(thr, dtype=torch.float64, device=probs.device)
-    ch = torch.tensor(chan, dtype=torch.int32, device=probs.device)
+    key = (probs.device, tuple(thr), tuple(chan))
+    if key not in _THRESHOLD_CONSTS:   # tiny device constants, created once (and never inside a graph capture)
+        _THRESHOLD_CONSTS[key] = (torch.tensor(thr, dtype=torch.float64, device=probs.device),
+                                  torch.tensor(chan, dtype=torch.int32, device=probs.device))
+    t, ch = _THRESHOLD_CONSTS[key]
     out = torch.empty((n, len(thr), h, w), dtype=torch.uint8, device=probs.device)
     L.fcall("mcb_threshold_layers", probs.data_ptr(), int(probs.dtype == torch.float64), t.data_ptr(), ch.data_ptr(),
             out.data_ptr(), n, c, len(thr), h, w)
@@ -317,12 +323,32 @@ class MaskPostprocessor:
         scores = scores_strided(labels.view(n * l, h, w), pr.view(n * l, h, w), counts, kcap)
         return labels, scores, counts, pr
 
+    def run_device_graphed(self, probs, kcap=1024):
+        """run_device replayed as ONE CUDA graph per (input shape, kcap): the chain is ~10 short launches whose host-side
+        launch cost exceeds their device time.  The returned tensors are STATIC buffers overwritten by the next call with
+        the same shape -- consume (or clone) them before calling again."""
+        key = (tuple(probs.shape), int(kcap))
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            static_in = probs.clone()
+            self.run_device(static_in, kcap)          # eager warm-up (module loading, allocator)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self.run_device(static_in, kcap)
+            ent = cache[key] = (g, static_in, outs)
+        g, static_in, outs = ent
+        static_in.copy_(probs, non_blocking=True)
+        g.replay()
+        return outs
+
     def transform(self, images, **_):
         probs = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.stack(images)))
         probs = probs.to(device=_dev(), dtype=torch.float32)
         kcap = 1024
         while True:
-            labels, scores, counts, _pr = self.run_device(probs, kcap)
+            labels, scores, counts, _pr = self.run_device_graphed(probs, kcap)
             cnt = counts.cpu().numpy()
             if cnt.size == 0 or int(cnt.max()) <= kcap:
                 break

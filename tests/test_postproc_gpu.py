@@ -141,3 +141,9 @@ def test_full_size_properties(G, cuda):
     ref = P.dilate_image(P.label_multilayer_image(P.categorize_multilayer_image(P.resize_image(probs[17].cpu().numpy(), (300, 300)))), 2)
     assert np.array_equal(labels[17].cpu().numpy(), ref)
     assert all(bool(torch.isfinite(scores[i, :cnts[i]]).all()) for i in range(128))
+    # the CUDA-graph replay of the same chain returns the same labels / counts, scores equal up to fp64 atomic order
+    for _ in range(2):
+        gl, gs, gc, _ = pp.run_device_graphed(probs)
+    assert torch.equal(gl, labels) and torch.equal(gc, counts)
+    for i in (0, 17, 127):
+        assert torch.allclose(gs[i, :cnts[i]], scores[i, :cnts[i]], rtol=1e-12, atol=0)

@@ -39,9 +39,11 @@ def ev(fn, n=5, warm=2):
 
 with torch.no_grad():
     t_fwd = ev(lambda: ops.softmax2(net(X)))
-t_pp = ev(lambda: pp.run_device(probs_syn))
+t_pp_eager = ev(lambda: pp.run_device(probs_syn))
+t_pp = ev(lambda: pp.run_device_graphed(probs_syn))
 pp_default = G.MaskPostprocessor((300, 300), mode, erode_selem_size=0, dilate_selem_size=0)  # neptune.yaml:69-70 defaults
-t_pp_default = ev(lambda: pp_default.run_device(probs_syn))
+t_pp_default_eager = ev(lambda: pp_default.run_device(probs_syn))
+t_pp_default = ev(lambda: pp_default.run_device_graphed(probs_syn))
 crop = probs_syn[:, :, 10:310, 10:310].contiguous() if s == 320 else G.resize_batch(probs_syn, (300, 300)).float()
 img = X[:, :, 10:310, 10:310].contiguous() if s == 320 else torch.randn(b, 3, 300, 300, device=dev)
 t_crf = ev(lambda: G.dense_crf_batch(img, crop), n=3, warm=1)
@@ -55,12 +57,13 @@ stages["erode+add_dropped(2)"] = ev(lambda: G.erode_batch(masks, 2))
 stages["label"] = ev(lambda: G.label_batch(masks))
 lab, cnt = G.label_batch(masks, return_counts=True)
 stages["dilate(2)"] = ev(lambda: G.morph_batch(lab, 2, True))
-stages["score"] = ev(lambda: G.scores_batch(lab.view(-1, 300, 300), pr.reshape(-1, 300, 300), cnt))
+stages["score"] = ev(lambda: G.scores_strided(lab.view(-1, 300, 300), pr.reshape(-1, 300, 300), cnt))
 if mode == "resize":
     stages["resize"] = ev(lambda: G.resize_batch(probs_syn, (300, 300)))
 out = {"workload": "UNetResNet-%d eval forward + softmax, batch %d @%dx%d, then mask post-processing to 300x300 (%s)" % (enc, b, s, s, mode),
        "forward_ms": round(t_fwd, 3), "postproc_ms": round(t_pp, 3), "postproc_share_of_step": round(t_pp / (t_fwd + t_pp), 4),
        "postproc_config": "erode 2 + dilate 2 (REPRODUCE_RESULTS.md evaluation setting)",
+       "postproc_eager_launch_ms": round(t_pp_eager, 3), "postproc_default_eager_launch_ms": round(t_pp_default_eager, 3),
        "postproc_default_ms": round(t_pp_default, 3),
        "postproc_default_share_of_step": round(t_pp_default / (t_fwd + t_pp_default), 4),
        "postproc_default_config": "erode 0 / dilate 0 (neptune.yaml defaults)",
