@@ -463,7 +463,7 @@ static int launch_wgrad(WgradParams& p, int cin_src, cudaStream_t st) {
   // operand streams: aim for `kb_target` K blocks per CTA, but keep at least a fraction of a wave busy
   const int kb_target = env_int("MCB_WGRAD_KB_TARGET", 64);
   if (kb_target > 0) {
-    const long lo_cap = cap * env_int("MCB_WGRAD_MIN_WAVE_X10", 5) / 10;
+    const long lo_cap = cap * env_int("MCB_WGRAD_MIN_WAVE_X10", 4) / 10;
     const int lo = (int)std::max(1L, lo_cap / std::max(1L, base));
     const int want = std::max(1, p.tiles_total / kb_target);
     splits = std::max(1, std::min(splits, std::max(lo, want)));
