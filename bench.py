@@ -151,8 +151,6 @@ def breakdown(step, n_iter=2):
         plan._stats_arena.zero_()
         evs = []
         for phase, o in ops:
-            if phase == "bwd" and not evs_bwd_started(evs):
-                pass
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             o()
@@ -181,10 +179,6 @@ def breakdown(step, n_iter=2):
                   "tflops": round(a[2] / (a[1] * 1e-3) / 1e12, 1) if a[2] else None,
                   "algo_gbs": round(a[3] / (a[1] * 1e-3) / 1e9, 1) if a[3] else None}
     return out, total
-
-
-def evs_bwd_started(evs):
-    return True
 
 
 _REAL_STDOUT = None

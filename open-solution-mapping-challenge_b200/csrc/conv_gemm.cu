@@ -460,7 +460,8 @@ static int launch_wgrad(WgradParams& p, int cin_src, cudaStream_t st) {
   const int min_kb = env_int("MCB_WGRAD_MIN_KB", 6);
   splits = std::max(1, std::min(splits, std::max(1, p.tiles_total / min_kb)));
   // short reductions (deep layers: few pixel tiles, many weights) are bound by the fp32 red.add epilogues, not by the
-  // operand streams: aim for `kb_target` K blocks per CTA, but keep at least a fraction of a wave busy
+  // operand streams: aim for `kb_target` K blocks per CTA, but keep at least 0.4 of a wave busy (tuned on the full
+  // step, where these GEMMs share the SMs with the BatchNorm-backward kernels: profiles/r01c_env_sweeps.log)
   const int kb_target = env_int("MCB_WGRAD_KB_TARGET", 64);
   if (kb_target > 0) {
     const long lo_cap = cap * env_int("MCB_WGRAD_MIN_WAVE_X10", 4) / 10;
