@@ -321,6 +321,19 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     note("e2e arm timed: %.3f ms/step" % ms_e2e)
 
+    # data-parallel sanity: every rank trains on different tiles, so the replicas stay identical only if the gradient
+    # all-reduce really happened -- a parameter checksum must agree across ranks (a step without the exchange would be
+    # faster and meaningless)
+    in_sync = None
+    if world > 1:
+        chk = model._net()._p32.double().sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        vals = [float(c) for c in allc]
+        in_sync = (max(vals) - min(vals)) <= 1e-9 * max(1.0, abs(vals[0]))
+        if not in_sync:
+            raise RuntimeError("replicas diverged (parameter checksums %r): gradient all-reduce missing?" % (vals,))
+
     tiles = args.batch * world
     value = tiles / (ms_dev * 1e-3)
     e2e = tiles / (ms_e2e * 1e-3)
@@ -340,6 +353,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": tiles, "parallelism": "dp%d" % world,
                    "bn": "per-replica batch statistics (reference DataParallel semantics)" if world > 1 else "batch statistics",
+                   "replicas_in_sync": in_sync,
                    "l2": "per-step working set (activations + gradients, GBs) far exceeds the 126 MB L2; no flush needed",
                    "loss_last_step": loss_dev},
         "e2e": {"value": round(e2e, 2), "unit": "tiles/s", "ms_per_step": round(ms_e2e, 4),

@@ -168,6 +168,11 @@ typedef struct {
 } mcb_bn_train;
 int mcb_bn_train_apply(const void* z, const mcb_bn_train* bn, const void* residual, const mcb_bn_train* res_bn, int relu,
                        void* y, long pixels, int c, float momentum, float eps, void* stream);
+/* Synchronised BatchNorm (one process per GPU): `stats` has been all-reduced over the ranks and stat_count = the GLOBAL
+   number of pixels per channel; `pixels` stays the local extent of z / y */
+int mcb_bn_train_apply_global(const void* z, const mcb_bn_train* bn, const void* residual, const mcb_bn_train* res_bn,
+                              int relu, void* y, long pixels, long stat_count, int c, float momentum, float eps,
+                              void* stream);
 /* backward: g = dy * (y_mask > 0);  dbeta += sum g;  dgamma += sum g * xhat */
 int mcb_bn_bwd_reduce(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
                       float* dbeta, float* dgamma, long pixels, int c, void* stream);
@@ -175,6 +180,10 @@ int mcb_bn_bwd_reduce(const void* dy, const void* y_mask, const void* z, const f
 int mcb_bn_bwd_apply(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
                      const float* gamma, const float* dbeta, const float* dgamma, void* dz, void* g_out,
                      int g_accumulate, long pixels, int c, void* stream);
+/* synchronised variant: dbeta / dgamma all-reduced over the ranks, M = stat_count (global pixels per channel) */
+int mcb_bn_bwd_apply_global(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
+                            const float* gamma, const float* dbeta, const float* dgamma, void* dz, void* g_out,
+                            int g_accumulate, long pixels, long stat_count, int c, void* stream);
 /* out[c] += sum over pixels of x[.., c]  (conv bias gradients) */
 int mcb_channel_sum(const void* x, float* out, long pixels, int c, void* stream);
 

@@ -90,6 +90,7 @@ _SIGS = {
     "mcb_bn_apply": [vp, vp, vp, vp, vp, vp, ci, vp, cl, ci, vp],
     "mcb_bn_bwd_reduce": [vp, vp, vp, vp, vp, vp, vp, cl, ci, vp],
     "mcb_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, cl, ci, vp],
+    "mcb_bn_bwd_apply_global": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, cl, cl, ci, vp],
     "mcb_channel_sum": [vp, vp, cl, ci, vp],
     "mcb_maxpool2_fwd": [vp, vp, ci, ci, ci, ci, vp],
     "mcb_maxpool2_bwd": [vp, vp, vp, ci, ci, ci, ci, ci, vp],
@@ -151,6 +152,8 @@ class BNTrain(C.Structure):
 
 lib.mcb_bn_train_apply.argtypes = [vp, C.POINTER(BNTrain), vp, C.POINTER(BNTrain), ci, vp, cl, ci, cf, cf, vp]
 lib.mcb_bn_train_apply.restype = ci
+lib.mcb_bn_train_apply_global.argtypes = [vp, C.POINTER(BNTrain), vp, C.POINTER(BNTrain), ci, vp, cl, cl, ci, cf, cf, vp]
+lib.mcb_bn_train_apply_global.restype = ci
 
 lib.mcb_bn_eval_params_batched.argtypes = [vp, ci, ci, cf, vp]
 lib.mcb_bn_eval_params_batched.restype = ci

@@ -741,6 +741,12 @@ extern "C" int mcb_bn_apply(const void* z, const float* scale, const float* shif
 extern "C" int mcb_bn_train_apply(const void* z, const mcb_bn_train* bn, const void* residual,
                                   const mcb_bn_train* res_bn, int relu, void* y, long pixels, int c, float momentum,
                                   float eps, void* stream) {
+  return mcb_bn_train_apply_global(z, bn, residual, res_bn, relu, y, pixels, pixels, c, momentum, eps, stream);
+}
+extern "C" int mcb_bn_train_apply_global(const void* z, const mcb_bn_train* bn, const void* residual,
+                                         const mcb_bn_train* res_bn, int relu, void* y, long pixels, long stat_count,
+                                         int c, float momentum, float eps, void* stream) {
+  MCB_REQUIRE(stat_count >= pixels, "bn_train_apply: stat_count %ld < pixels %ld", stat_count, pixels);
   MCB_REQUIRE(z && bn && y && bn->stats && bn->gamma && bn->beta && bn->mean && bn->invstd, "bn_train_apply: null pointer");
   MCB_REQUIRE(c % 8 == 0 && 256 % (c / 8) == 0, "bn_train_apply: channels %d (c/8 must divide 256)", c);
   MCB_REQUIRE(!(res_bn && !residual), "bn_train_apply: res_bn without residual");
@@ -750,7 +756,7 @@ extern "C" int mcb_bn_train_apply(const void* z, const mcb_bn_train* bn, const v
   BNTrain rb{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (res_bn) rb = BNTrain{res_bn->stats, res_bn->gamma, res_bn->beta, res_bn->running_mean, res_bn->running_var,
                            res_bn->mean, res_bn->invstd};
-  const float count = (float)pixels;
+  const float count = (float)stat_count;
   if (residual == nullptr)
     launch_pdl(bn_train_apply_kernel<0>, grid, 256, 0, ST, (const uint4*)z, b, nullptr, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
   else if (res_bn == nullptr)
@@ -794,12 +800,20 @@ extern "C" int mcb_bn_bwd_reduce(const void* dy, const void* y_mask, const void*
 extern "C" int mcb_bn_bwd_apply(const void* dy, const void* y_mask, const void* z, const float* mean,
                                 const float* invstd, const float* gamma, const float* dbeta, const float* dgamma,
                                 void* dz, void* g_out, int g_accumulate, long pixels, int c, void* stream) {
+  return mcb_bn_bwd_apply_global(dy, y_mask, z, mean, invstd, gamma, dbeta, dgamma, dz, g_out, g_accumulate, pixels,
+                                 pixels, c, stream);
+}
+extern "C" int mcb_bn_bwd_apply_global(const void* dy, const void* y_mask, const void* z, const float* mean,
+                                       const float* invstd, const float* gamma, const float* dbeta, const float* dgamma,
+                                       void* dz, void* g_out, int g_accumulate, long pixels, long stat_count, int c,
+                                       void* stream) {
+  MCB_REQUIRE(stat_count >= pixels, "bn_bwd_apply: stat_count %ld < pixels %ld", stat_count, pixels);
   MCB_REQUIRE(dy && z && mean && invstd && gamma && dbeta && dgamma && dz, "bn_bwd_apply: null pointer");
   MCB_REQUIRE(c % 8 == 0, "bn_bwd_apply: channels %d", c);
   MCB_REQUIRE(256 % (c / 8) == 0, "bn_bwd_apply: channels %d (c/8 must divide 256)", c);
   const long total8 = pixels * (c / 8);
   const int grid = grid_for((total8 + 1) / 2, 256);
-  const float ic = 1.0f / (float)pixels;
+  const float ic = 1.0f / (float)stat_count;
 #define MCB_BWD(MASK, GOUT)                                                                                         \
   launch_pdl(bn_bwd_apply_kernel<MASK, GOUT>, grid, 256, 0, ST, (const uint4*)dy, (const uint4*)y_mask, (const uint4*)z, mean, \
                                                         invstd, gamma, dbeta, dgamma, ic, (uint4*)dz, (uint4*)g_out,  \

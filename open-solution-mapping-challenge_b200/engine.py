@@ -9,6 +9,7 @@ split-K wgrad GEMMs; decoder ReLU masks are applied in the dgrad epilogues; skip
 accumulated with TMA reduce-add."""
 import os
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from . import ops
@@ -70,6 +71,14 @@ class Plan:
         self._stats_used = 0
         self.graph_fwd = self.graph_bwd = None
         self._side = None
+        # Synchronised BatchNorm (opt-in, MCB_SYNC_BN=1, one process per GPU): every BatchNorm normalises with the
+        # statistics of the GLOBAL batch -- [sum, sum^2] all-reduced between the conv that produces them and the BN
+        # apply pass, [dbeta, dgamma] all-reduced before the dz pass.  The default keeps the reference's DataParallel
+        # semantics (per-replica statistics, src/models.py:65).  The collectives are issued from the plan, so they are
+        # captured into the step's CUDA graphs with everything else.
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.sync_bn = training and self.world > 1 and os.environ.get("MCB_SYNC_BN", "0") == "1"
+        self.bn_scale = self.world if self.sync_bn else 1
         self.bias_sum = {}         # id(conv+bias+ReLU output) -> its bias-gradient vector (fused into the consumer's dgrad)
         self.bias_fused = set()
         self.x_in = torch.zeros((n, 3, h, w), dtype=F32, device=self.dev)
@@ -138,6 +147,7 @@ class Plan:
         desc = "%d->%d k%d s%d @%dx%dx%d" % (cin, cout, k, s, n, h, w)
         if self.training:
             F.add("conv_fwd", lambda: ops.conv_fwd(x, w16, k, s, stats=bn.stats, out=z), cflops, _nb(x, w16, z), desc)
+            self.sync_stats(F, bn)
         else:
             # inference: BatchNorm is a per-channel affine known up front -> folded into the conv epilogue together with
             # the residual add and the ReLU; no pre-BN tensor is materialised (z IS the block output here)
@@ -156,13 +166,36 @@ class Plan:
         F = self.fwd_ops
         if self.training:
             rtr = res_bn.tr if res_bn is not None else None
-            F.add("bn_apply", lambda: ops.bn_train_apply(z, bn.tr, y, relu, residual, rtr, BN_MOMENTUM, BN_EPS), 0,
-                  _nb(z, y, residual))
+            F.add("bn_apply", lambda: ops.bn_train_apply(z, bn.tr, y, relu, residual, rtr, BN_MOMENTUM, BN_EPS,
+                                                         self.bn_scale), 0, _nb(z, y, residual))
         elif res_bn is not None:
             F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, res_bn.scale,
                                                    res_bn.shift), 0, _nb(z, y, residual))
         else:
             F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual), 0, _nb(z, y, residual))
+
+    def sync_stats(self, F, bn):
+        """SyncBN forward: sum the per-rank [sum, sum^2] before the BN apply pass reads them"""
+        if self.sync_bn:
+            F.add("bn_allreduce", lambda: dist.all_reduce(bn.stats))
+
+    def sync_bn_grads(self, B, bn):
+        """SyncBN backward: dz needs the GLOBAL dbeta / dgamma.  They are the parameter-gradient slots themselves, so
+        after this they hold the global sums on every rank (FusedTrainStep divides them by the world size before the
+        arena-wide gradient all-reduce adds the ranks up again)."""
+        if self.sync_bn:
+            g32 = self.net._g32
+            lo = (bn.dgamma.data_ptr() - g32.data_ptr()) // 4
+            hi = (bn.dbeta.data_ptr() - g32.data_ptr()) // 4
+            if hi == lo + bn.c:       # gamma and beta slots are adjacent: one collective
+                both = g32[lo:lo + 2 * bn.c]
+                B.add("bn_allreduce", lambda: dist.all_reduce(both))
+            else:
+                B.add("bn_allreduce", lambda: (dist.all_reduce(bn.dgamma), dist.all_reduce(bn.dbeta)))
+
+    def bn_grad_slices(self):
+        """views of every BatchNorm weight/bias gradient in the arena (see sync_bn_grads)"""
+        return [t for b in self._bns for t in (b.dgamma, b.dbeta)]
 
     def conv_unit_backward(self, B, dy, ymask, z, bn, conv, x, g_out=None, g_out_acc=False, reduced=False):
         """backward of y = relu(bn(conv(x)) [+ r]) given dy = dL/dy: BN reductions + dz, wgrad, dgrad into grad(x).
@@ -175,8 +208,10 @@ class Plan:
         if not reduced:  # else: the dgrad that produced dy already accumulated dbeta / dgamma in its epilogue
             B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma),
                   0, _nb(dy, ymask, z))
+        self.sync_bn_grads(B, bn)
         B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma,
-                                                      dz, g_out, g_out_acc), 0, _nb(dy, ymask, z, dz, g_out))
+                                                      dz, g_out, g_out_acc, self.bn_scale), 0,
+              _nb(dy, ymask, z, dz, g_out))
         desc = "%d->%d k%d s%d @%dx%dx%d" % (x.shape[3], dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2])
         B.add("conv_wgrad", lambda: ops.conv_wgrad(dz, x, gw, k, s), 2.0 * dz.numel() * x.shape[3] * k * k,
               _nb(dz, x, gw), desc)
@@ -228,6 +263,7 @@ class Plan:
         bn0 = self.bn_state(enc.bn1)
         if train:
             F.add("conv_fwd", lambda: ops.conv_fwd(col, stem_w16, 1, 1, stats=bn0.stats, out=z0), sflops, _nb(col, z0))
+            self.sync_stats(F, bn0)
             a0 = self.act(*z0.shape)
             self.bn_apply_op(z0, bn0, a0, True)
         else:
@@ -247,8 +283,10 @@ class Plan:
                 B.add("maxpool", lambda: ops.maxpool2_bwd(a0, d_c1, d_a0, False), 0, _nb(a0, d_c1, d_a0))
                 B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.dbeta,
                                                                 bn0.dgamma), 0, _nb(d_a0, a0, z0))
+                self.sync_bn_grads(B, bn0)
                 B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma,
-                                                              bn0.dbeta, bn0.dgamma, dz0), 0, _nb(d_a0, a0, z0, dz0))
+                                                              bn0.dbeta, bn0.dgamma, dz0, None, False, self.bn_scale),
+                      0, _nb(d_a0, a0, z0, dz0))
                 B.add("misc", lambda: stem_gw.zero_())
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1), sflops, _nb(dz0, col))
                 B.add("misc", lambda: ops.stem_unpack_wgrad(stem_gw, stem_g))

@@ -364,7 +364,7 @@ class FusedTrainStep:
         self.segments = None
         # opt-in: on 2 GPUs the three smaller all-reduces + graph segmentation cost more than they hide (22.8 vs 22.3
         # ms/step, gpurun r1); kept for larger worlds / slower fabrics
-        if self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "1":
+        if self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "1" and not self.plan.sync_bn:
             self.segments = self.plan.bwd_segments()
             self._comm_stream = torch.cuda.Stream(device=dev)
         # single GPU: the Adam update of a finished arena segment (decoder | layer4 | rest) rides on the backward's side
@@ -487,6 +487,12 @@ class FusedTrainStep:
                 self._seg_backward()
             else:
                 self.graphs[1].replay()
+            if self.world > 1:
+                if self.plan.sync_bn:
+                    # the BatchNorm slots already hold GLOBAL sums (engine.Plan.sync_bn_grads): pre-divide so that the
+                    # arena-wide SUM below leaves them unchanged
+                    torch._foreach_mul_(self.plan.bn_grad_slices(), 1.0 / self.world)
+                dist.all_reduce(self.net._g32)   # gradients of the global-batch loss = sum of the per-rank contributions
         else:
             # bucketed gradient all-reduce: segment k's arena range is reduced on the NCCL stream while segment k+1 runs
             main = torch.cuda.current_stream()

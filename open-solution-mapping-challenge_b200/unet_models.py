@@ -206,6 +206,9 @@ class UNetResNet(nn.Module):
         x = x.contiguous().float()
         pl = self.plan(x.shape[0], x.shape[2], x.shape[3], self.training)
         if torch.is_grad_enabled() and self.training:
+            if pl.sync_bn:
+                raise NotImplementedError("MCB_SYNC_BN needs the fused train step (mcb200.models.PyTorchUNet*): the "
+                                          "autograd bridge leaves gradient reduction to the caller")
             from .engine import UNetFunction
             return UNetFunction.apply(x, self, pl, *[p for _, p, _ in self._arena_params()])
         self.refresh_operands()
