@@ -51,6 +51,7 @@ def two_gpus(cuda):
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
 
 
+@pytest.mark.timeout(600)
 def test_replicas_stay_identical_with_per_replica_batchnorm(mcb, two_gpus):
     r0, r1 = _run_two_ranks(sync_bn=False)
     assert r0["losses"] == r1["losses"]                   # the loss is global-batch on every rank
@@ -59,6 +60,10 @@ def test_replicas_stay_identical_with_per_replica_batchnorm(mcb, two_gpus):
     assert r0["losses"][-1] < r0["losses"][0]
 
 
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(os.environ.get("MCB_TEST_SYNC_BN") != "1",
+                    reason="synchronised BatchNorm is an opt-in that has not run on hardware yet (DESIGN.md section 5): "
+                           "set MCB_TEST_SYNC_BN=1 on a >= 2-GPU box")
 def test_sync_bn_reproduces_the_single_process_global_batch(mcb, two_gpus):
     import bench
     from mcb200.models import PyTorchUNetWeighted
