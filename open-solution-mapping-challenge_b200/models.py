@@ -370,6 +370,8 @@ class FusedTrainStep:
         # single GPU: the Adam update of a finished arena segment (decoder | layer4 | rest) rides on the backward's side
         # stream, inside the graph, overlapping the data-gradient GEMMs of the layers below (HBM-bound next to
         # tensor-bound).  Its step-dependent scalars live in a 3-float device tensor refreshed before every replay.
+        self.inline_allreduce = (self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "2"
+                                 and not self.plan.sync_bn)
         self.adam_in_graph = self.world == 1 and os.environ.get("MCB_ADAM_SIDE", "1") == "1"
         self._hyper = torch.zeros(3, dtype=torch.float32, device=dev)
         # pinned staging ring: a slot is rewritten only after the copy that last read it has executed
@@ -401,7 +403,18 @@ class FusedTrainStep:
                     return lambda: ops.adam_step_dyn(net._p32[lo:hi], net._g32[lo:hi], self.m[lo:hi], self.v[lo:hi],
                                                      net._w16[lo:hi], self._hyper, betas, eps, wd, 1.0)
                 hooks = {last: upd(lo, hi) for _, last, lo, hi in self.plan.bwd_segments()}
+            works = []
+            if self.inline_allreduce:
+                # MCB_OVERLAP_ALLREDUCE=2 (experimental, not yet run on hardware): the all-reduce of a finished arena
+                # segment is issued from INSIDE the single backward graph, on the side stream behind that segment's
+                # weight-gradient GEMMs, and overlaps the data-gradient chain of the layers below; the main stream joins
+                # the collectives at the end of the graph
+                g32 = self.net._g32
+                hooks = {last: (lambda lo=lo, hi=hi: works.append(dist.all_reduce(g32[lo:hi], async_op=True)))
+                         for _, last, lo, hi in self.plan.bwd_segments()}
             self.plan._run_bwd(hooks=hooks)
+            for wk in works:
+                wk.wait()
         else:
             self.plan._run_bwd(seg[0], seg[1])
 
@@ -487,7 +500,7 @@ class FusedTrainStep:
                 self._seg_backward()
             else:
                 self.graphs[1].replay()
-            if self.world > 1:
+            if self.world > 1 and not self.inline_allreduce:
                 if self.plan.sync_bn:
                     # the BatchNorm slots already hold GLOBAL sums (engine.Plan.sync_bn_grads): pre-divide so that the
                     # arena-wide SUM below leaves them unchanged
