@@ -75,6 +75,11 @@ static int launch_conv(int BN, int BK, bool b_mn, ConvGemmParams& p, int m_tiles
   const int fixed = out_bytes + stat_bytes + 1024 /*align*/ + 1536 /*barriers, row tables*/ + (halo ? 2 * a_bytes : 0);
   const int budget = std::min(env_int("MCB_SMEM_BUDGET_KB", 227) * 1024, 232448);
   int stages = std::max(2, std::min(env_int("MCB_MAX_STAGES", halo ? 9 : 6), (budget - fixed) / stage));
+  if (p.b_resident) {
+    // resident weights need one ring slot per tap, a single N tile and a single phase
+    if (halo && n_tiles == 1 && phases == 1 && (budget - fixed) / stage >= 9) stages = 9;
+    else p.b_resident = 0;
+  }
   p.stages = stages;
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.phases = phases;
   const size_t smem = (size_t)stages * stage + fixed;
@@ -96,6 +101,9 @@ static int launch_conv(int BN, int BK, bool b_mn, ConvGemmParams& p, int m_tiles
 static bool use_halo(int ksize, int stride, int W, int H, int k_channels) {
   const int mode = env_int("MCB_HALO", 2);
   if (ksize != 3 || stride != 1 || mode == 0) return false;
+  // experimental (MCB_BRES=1, not yet run on hardware): one-chunk layers (32 / 64 channels) take the haloed tile with
+  // RESIDENT weights -- one TMA load and 18 / 36 back-to-back MMAs per tile instead of 18 loads and 9 barrier waits
+  if (env_int("MCB_BRES", 0) == 1 && k_channels <= 64 && W % 8 == 0 && H % 16 == 0) return true;
   if (mode == 2) return k_channels >= env_int("MCB_HALO_MINC", 128) && W % 8 == 0 && H % 16 == 0 && W >= 80;
   const double eff = (double)W * H / ((double)((W + 7) / 8) * 8 * ((H + 15) / 16) * 16);
   return eff >= 0.8;
@@ -230,6 +238,7 @@ extern "C" int mcb_conv_fwd(const mcb_conv_fwd_args* a, void* stream) {
                                out_cw * 2)) return r;
   p.bias = a->bias; p.relu = a->relu; p.stats = a->stats; p.stats_c = a->cout;
   p.scale = a->scale;
+  p.b_resident = (halo && nsrc == 1 && a->cin[0] == BK && env_int("MCB_BRES", 0) == 1) ? 1 : 0;
   if (a->residual) {
     p.residual = static_cast<const __nv_bfloat16*>(a->residual);
     p.mask_H = Ho; p.mask_W = Wo; p.mask_C = a->cout; p.mask_s = 1;
@@ -323,6 +332,7 @@ extern "C" int mcb_conv_dgrad(const mcb_conv_dgrad_args* a, void* stream) {
                                    out_cw * 2)) return r;
   }
   p.accumulate = a->accumulate;
+  p.b_resident = (halo && a->cout == BK && env_int("MCB_BRES", 0) == 1) ? 1 : 0;
   p.aux_mode = a->bn_z ? 2 : (a->relu_mask ? 1 : 0);
   MCB_REQUIRE(!(a->dx_channel_sum && (!a->relu_mask || a->accumulate)),
               "conv_dgrad: dx_channel_sum needs relu_mask and a complete (non-accumulated) gradient");

@@ -41,6 +41,8 @@ struct ConvGemmParams {
   int tiles_x, tiles_y;
   int m_tiles, n_tiles, phases;  // persistent tile space: phases x m_tiles x n_tiles
   int stages;
+  int b_resident;  // HALO only, experimental: the 9 per-tap weight tiles are loaded ONCE per CTA into ring slots 0..8
+                   // (single N tile, one channel chunk) instead of once per pixel tile
   int n_off;  // first N (weight row / column) coordinate of this launch (concat source slice for dgrad)
   // epilogue:  v = acc * scale[c] + bias[c] + residual[pix][c];  v = relu(v);  v = mask ? v : 0
   const float* scale;              // per-channel multiplier (inference-mode BatchNorm folded into the epilogue), or null
@@ -222,10 +224,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               }
               for (int t = 0; t < 9; ++t, ++kb) {
                 const TapDesc tap = p.taps[tap_begin + t * nsrc + sidx];
-                const int s = ring_s;
+                int s = ring_s;
                 const uint32_t ph = ring_ph;
                 if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
-                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                if (p.b_resident) {
+                  if (ag != 0) continue;   // weights of tap t already sit in slot t
+                  s = t;
+                } else {
+                  tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                }
                 uint8_t* sb = smem + (size_t)s * STAGE_BYTES;
                 if (tc::elect_one()) {
                   tc::mbar_expect_tx(&full_bar[s], B_BYTES);
@@ -296,10 +303,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             const uint32_t a_base = tc::smem_u32(a_ring + (size_t)as * A_BYTES);
             for (int t = 0; t < 9; ++t, ++kb, ++i) {
               const TapDesc tap = p.taps[tap_begin + t * nsrc + sidx];
-              const int s = ring_s;
+              int s = ring_s;
               const uint32_t ph = ring_ph;
               if (++ring_s == stages) { ring_s = 0; ring_ph ^= 1; }
-              tc::mbar_wait(&full_bar[s], ph);
+              if (p.b_resident) {
+                s = t;
+                if (ag == 0) tc::mbar_wait(&full_bar[s], 0);   // first tile of this CTA only
+              } else {
+                tc::mbar_wait(&full_bar[s], ph);
+              }
               tc::tc_fence_after();
               if (tc::elect_one()) {
                 const uint32_t sa = a_base + (uint32_t)(((1 + tap.dy) * kHaloW + (1 + tap.dx)) * A_ROW_BYTES);
@@ -314,7 +326,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
                   const uint64_t db = B_MN ? db0 + (uint64_t)((k * 16 * BMN_ROW_BYTES) >> 4) : db0 + (uint64_t)((k * 32) >> 4);
                   tc::umma_bf16(tmem_acc, da, db, IDESC, (i > 0 || k > 0) ? 1u : 0u);
                 }
-                tc::umma_commit(&empty_bar[s]);
+                if (!p.b_resident) tc::umma_commit(&empty_bar[s]);
                 if (t == 8) tc::umma_commit(&a_empty_bar[as]);
                 if (i == num_kb - 1) tc::umma_commit(&tmem_full_bar[acc]);
               }

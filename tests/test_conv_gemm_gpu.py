@@ -4,6 +4,8 @@ torch's fp32 CPU convolution — the op the reference calls (nn.Conv2d / nn.Conv
 
 Tolerance: outputs are stored as bf16 (8 mantissa bits) after fp32 accumulation, so |err| <= 2^-8 |ref| + small
 accumulation-order noise; integer-valued cases must match exactly."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -90,11 +92,25 @@ def test_conv_fwd_integer_exact(mcb, cuda):
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 16, 64, 128), (1, 32, 24, 128, 64), (1, 16, 16, 32, 32),
                                              (2, 20, 20, 64, 64)])
 def test_conv3x3_haloed_tile_path(mcb, cuda, monkeypatch, n, h, w, cin, cout):
+    _haloed_tile_checks(cuda, monkeypatch, n, h, w, cin, cout, resident=False)
+
+
+@pytest.mark.skipif(os.environ.get("MCB_TEST_EXPERIMENTAL") != "1",
+                    reason="MCB_BRES (resident per-tap weights in the haloed path) has not run on hardware yet")
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 16, 64, 64), (1, 32, 24, 32, 32), (3, 16, 16, 32, 32),
+                                             (2, 48, 40, 64, 128)])
+def test_conv3x3_haloed_tile_resident_weights(mcb, cuda, monkeypatch, n, h, w, cin, cout):
+    _haloed_tile_checks(cuda, monkeypatch, n, h, w, cin, cout, resident=True)
+
+
+def _haloed_tile_checks(cuda, monkeypatch, n, h, w, cin, cout, resident):
     """MCB_HALO=1 forces the haloed-tile 3x3 path (one TMA box per channel chunk serves the nine taps through
     row-shifted UMMA descriptors; default rule: >= 128 channels on large images): forward (+stats, integer-exact),
     plain / masked data gradient, against the same references as the per-tap path"""
     from mcb200 import ops
     monkeypatch.setenv("MCB_HALO", "1")
+    if resident:
+        monkeypatch.setenv("MCB_BRES", "1")
     g = torch.Generator().manual_seed(11 + h + cin)
     x = torch.randint(-1, 2, (n, cin, h, w), generator=g).float()
     wt = (torch.rand(cout, cin, 3, 3, generator=g) < 0.1).float() * torch.randint(-1, 2, (cout, cin, 3, 3), generator=g)
