@@ -301,6 +301,26 @@ class MaskPostprocessor:
         self.erode, self.dilate = erode_selem_size, dilate_selem_size
         self.category_layers = category_layers or CATEGORY_LAYERS
 
+    # BaseTransformer contract (src/steps/base.py:254-269): stateless, so fit is a no-op and save/load persist nothing
+    def fit(self, *args, **kwargs):
+        return self
+
+    def fit_transform(self, *args, **kwargs):
+        self.fit(*args, **kwargs)
+        return self.transform(*args, **kwargs)
+
+    def load(self, filepath):
+        return self
+
+    def save(self, filepath):
+        import joblib
+        joblib.dump({}, filepath)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_graphs", None)     # captured CUDA graphs and their static buffers are rebuilt on demand
+        return state
+
     def run_device(self, probs, kcap=1024):
         """probs (N, C, S, S) float32 cuda -> (labels int32 (N,L,H,W), scores float64 (N*L, kcap), counts int32 (N*L,),
         probabilities used).  No host synchronisation inside."""

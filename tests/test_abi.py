@@ -38,3 +38,18 @@ def test_compute_entry_points_fail_loudly_without_gpu(mcb):
     from mcb200 import postprocessing as pp
     with pytest.raises(RuntimeError):
         pp.label_multilayer_image(__import__("numpy").zeros((2, 8, 8), bool))
+
+
+def test_postprocessor_honours_the_step_transformer_contract(tmp_path):
+    """src/steps/base.py:254-269: a Step calls fit_transform / save / load on its transformer and may pickle it"""
+    import pickle
+    import mcb200  # noqa: F401
+    from mcb200.postprocessing import MaskPostprocessor
+    pp = MaskPostprocessor((300, 300), "crop", 2, 2)
+    assert pp.fit() is pp and pp.load(str(tmp_path / "x")) is pp
+    pp.save(str(tmp_path / "pp.pkl"))
+    assert (tmp_path / "pp.pkl").exists()
+    pp.__dict__["_graphs"] = {"k": object()}          # stands in for captured graphs
+    clone = pickle.loads(pickle.dumps(pp))
+    assert clone.target_size == (300, 300) and clone.mode == "crop" and (clone.erode, clone.dilate) == (2, 2)
+    assert "_graphs" not in clone.__dict__
