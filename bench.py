@@ -4,6 +4,11 @@
   python bench.py --gpus N --steps K --warmup W          our arm: ResNet101-UNet train step, batch 32/GPU, 300x300
                                                           tiles replicate-padded to the 320x320 net input
   python bench.py --impl reference ...                    the reference's CPU path (oracle port) on the host cores
+  python bench.py --impl torch_cudnn ...                  LIBRARY baseline: the same net / step in stock PyTorch (cuDNN,
+                                                          channels_last, bf16 autocast, fused Adam) on the same GPU
+  python bench.py --workload infer ...                    BASELINE.json configs[3]: eval forward + full post-processing
+                                                          (dense CRF, threshold, erode, label, dilate, score, watershed),
+                                                          batch 64, host images in -> host label maps out
 
 One JSON line on stdout (rank 0).  `value` = tiles/s with inputs resident in HBM; `e2e` = the same metric through the
 reference-facing API (PyTorchUNetWeighted._fit_loop on pinned HOST batches, loss read back every step)."""
@@ -116,7 +121,8 @@ def cpu_reference_arm(args, sample_batch=None, steps=None, warmup=None):
     """the reference's own CPU implementation of the train step (oracle port of Model._fit_loop, fp32, all host
     threads) on a bounded sample of the workload"""
     import torch
-    from oracle import unet_oracle as O, synthetic
+    from oracle import unet_oracle as O
+    import bench_data as synthetic
     cores = usable_cores()
     torch.set_num_threads(cores)
     b = sample_batch or max(1, min(args.batch, 4))
@@ -138,7 +144,8 @@ def cpu_reference_arm(args, sample_batch=None, steps=None, warmup=None):
     dt = (time.time() - t0) / steps
     return {"value": b / dt, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "oracle port of Model._fit_loop (fp32 torch CPU), UNetResNet-%d, batch %d @%dx%d, %d warm-up + %d timed steps"
-                      % (args.encoder, b, args.size, args.size, warmup, steps), "ms_per_step": dt * 1e3}
+                      % (args.encoder, b, args.size, args.size, warmup, steps), "ms_per_step": dt * 1e3,
+            "steps_run": steps, "warmup_run": warmup, "batch_run": b}
 
 
 def breakdown(step, n_iter=2):
@@ -181,6 +188,279 @@ def breakdown(step, n_iter=2):
     return out, total
 
 
+def library_baseline(args, dev, Xd, Td, steps=10, warmup=3):
+    """stock PyTorch on the same GPU: baseline/torch_cudnn_unet.py (cuDNN, channels_last, bf16 autocast, fused Adam)"""
+    import torch
+    from baseline.torch_cudnn_unet import TrainStep
+    try:
+        ts = TrainStep(args.encoder, dev)
+        for _ in range(warmup):
+            ts.step(Xd, Td)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = ts.step(Xd, Td)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"value": round(Xd.shape[0] / (ms * 1e-3), 2), "unit": "tiles/s", "ms_per_step": round(ms, 4),
+               "steps": steps, "warmup": warmup, "loss_last_step": float(loss),
+               "what": "torch %s eager: torchvision ResNet-%d U-Net, cuDNN %s, channels_last, bf16 autocast, "
+                       "torch.optim.Adam(fused=True), same batch / size / loss; inputs resident in HBM"
+                       % (torch.__version__, args.encoder, torch.backends.cudnn.version())}
+        del ts
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # the baseline must never take the product's bench line down with it
+        return {"value": None, "error": "%s: %s" % (type(e).__name__, e)}
+
+
+def library_baseline_line(args, dev, rank, world, workload):
+    """--impl torch_cudnn: the library baseline as its own bench line (same metric / config / timing rules)"""
+    import torch
+    import torch.distributed as dist
+    import bench_data as synthetic
+    x, t = synthetic.train_batch(args.batch, args.size, seed=1234 + rank)
+    Xd, Td = torch.from_numpy(x).to(dev), torch.from_numpy(t).to(dev)
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    lb = library_baseline(args, dev, Xd, Td, steps=args.steps, warmup=args.warmup)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:   # independent replicas (no gradient exchange): a generous upper bound for DDP
+        v = torch.tensor([lb["ms_per_step"] or 0.0], device=dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        lb["ms_per_step"] = float(v)
+        lb["value"] = args.batch / (lb["ms_per_step"] * 1e-3)
+    peak_tf, _, peak_src = peaks()
+    fpt = FLOP_PER_TILE.get((args.encoder, args.size))
+    achieved = (lb["value"] or 0) * (fpt or 0) / 1e12
+    return {"impl": "torch_cudnn", "metric": "300x300 tiles/sec fwd+bwd ResNet101-UNet",
+            "value": round((lb["value"] or 0) * world, 2), "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": lb.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": args.batch * world,
+                       "parallelism": "dp%d (independent replicas, no gradient exchange)" % world, "what": lb.get("what")},
+            "clocks": clocks, "gpu_launches": 0,
+            "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src},
+            "error": lb.get("error")}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# --workload infer: BASELINE.json configs[3]
+# ------------------------------------------------------------------------------------------------------------------
+INFER_METRIC = "300x300 tiles/sec inference + full post-processing ResNet101-UNet"
+POST_BYTES_PER_IMAGE = 1.44e6   # SURVEY.md 8d: 2x300x300 fp32 probabilities in, 2x300x300 int32 labels out
+
+
+def infer_workload_name(args):
+    return ("UNetResNet-%d eval forward + softmax, batch %d/GPU, 300x300 tiles replicate-padded to %dx%d, then per image: "
+            "centre crop -> dense CRF (5 mean-field iterations) -> resize_image (identity size, fp64) -> threshold -> erode 2 -> label -> dilate 2 -> score, "
+            "and a marker watershed split of the refined building probability" % (args.encoder, args.batch, args.size,
+                                                                                args.size))
+
+
+def infer_line(args, dev, rank, world):
+    """inference + the full per-pixel chain.  `value`: inputs resident in HBM, results left on the device.  `e2e`:
+    pinned HOST images in, HOST label maps / scores / watershed labels out, copies inside the timed region."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bench_data as synthetic
+    from mcb200 import ops, postprocessing as G
+    from mcb200.models import PyTorchUNet
+    b, s = args.batch, args.size
+    torch.manual_seed(1234)
+    model = PyTorchUNet(**unet_config("ResNet%d" % args.encoder))
+    model._to_device()
+    net = model.model
+    net.eval()
+    x, _ = synthetic.train_batch(b, s, seed=1234 + rank)
+    Xh = torch.from_numpy(x).pin_memory()
+    Xd = Xh.to(dev)
+    # a random-init net predicts noise: the chain is fed building-like probability maps of the same shape / dtype
+    # (the forward pass still runs on X every step; its output is blended out with weight 0 so that the dependency stays)
+    syn = torch.from_numpy(synthetic.probability_maps(b, s, seed=7 + rank)).to(dev)
+    mode = "crop" if s == 320 else "resize"
+    pp = G.MaskPostprocessor((300, 300), "resize", erode_selem_size=2, dilate_selem_size=2)
+    m0 = (s - 300) // 2 if mode == "crop" else 0
+    timing = {}
+
+    def chain(X, record=False):
+        evs = []
+
+        def mark(name):
+            if record:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append((name, e))
+        mark("start")
+        with torch.no_grad():
+            probs = ops.softmax2(net(X))
+        mark("forward+softmax")
+        probs = probs * 0.0 + syn
+        if mode == "crop":   # prediction_crop (src/pipelines.py:44-60), then the chain's own identity-sized mask_resize
+            pc = probs[:, :, m0:s - m0, m0:s - m0].contiguous()
+            img = X[:, :, m0:s - m0, m0:s - m0].contiguous()
+        else:
+            pc, img = probs, X
+        mark("crop")
+        refined = G.dense_crf_batch(img, pc)
+        mark("dense_crf")
+        labels, scores, counts, _pr = pp.run_device_graphed(refined)
+        mark("resize+threshold+erode+label+dilate+score")
+        ws = G.watershed_split(refined[:, 1].contiguous(), hi=0.8, lo=0.5)
+        mark("watershed")
+        if record:
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+                timing[n1] = timing.get(n1, 0.0) + e0.elapsed_time(e1)
+        return labels, scores, counts, ws
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(args.warmup):
+        chain(Xd)
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev = timed(lambda: chain(Xd), args.steps)
+    clocks = sampler.stop() if sampler else None
+    n_rec = 3
+    for _ in range(n_rec):
+        chain(Xd, record=True)
+    stages = {k: round(v / n_rec, 4) for k, v in timing.items()}
+
+    # end to end: host images in, host results out (pinned, reused buffers)
+    out_h = {}
+
+    def step_e2e():
+        X = Xh.to(dev, non_blocking=True)
+        labels, scores, counts, ws = chain(X)
+        for k, t in (("labels", labels), ("scores", scores), ("counts", counts), ("ws", ws)):
+            if k not in out_h:
+                out_h[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            out_h[k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller owns the results when the call returns
+
+    for _ in range(args.warmup):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    d2h = int(sum(t.numel() * t.element_size() for t in out_h.values()))
+    if rank != 0:
+        return None
+    _, peak_hbm, peak_src = peaks()
+    post_ms = sum(v for k, v in stages.items() if k not in ("forward+softmax",))
+    chain_ms = stages.get("resize+threshold+erode+label+dilate+score", 0.0)
+    tiles = b * world
+    line = {
+        "metric": INFER_METRIC, "value": round(tiles / (ms_dev * 1e-3), 2), "unit": "tiles/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (network) / f32, u8, i32 (post-processing)", "data": "synthetic",
+        "config": {"workload": infer_workload_name(args), "global_batch": tiles, "parallelism": "dp%d replicas" % world,
+                   "l2": "the batch's maps (92 MB of probabilities + labels, GBs of activations) exceed the 126 MB L2"},
+        "e2e": {"value": round(tiles / (ms_e2e * 1e-3), 2), "unit": "tiles/s", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": int(Xh.numel() * 4), "d2h_bytes_per_step": d2h,
+                "api": "PyTorchUNet net forward on pinned host images -> MaskPostprocessor + dense_crf_batch + "
+                       "watershed_split -> pinned host labels / scores / counts / watershed labels"},
+        "gpu_launches": None, "clocks": clocks,
+        "stages_ms": stages,
+        "postproc": {"ms_all_stages": round(post_ms, 4), "share_of_step_all_stages": round(post_ms / (post_ms + stages["forward+softmax"]), 4),
+                     "ms_reference_chain": round(chain_ms, 4),
+                     "share_of_step_reference_chain": round(chain_ms / (chain_ms + stages["forward+softmax"]), 4),
+                     "note": "reference chain = what src/pipelines.py:248-304 runs (threshold, erode, label, dilate, score); "
+                             "dense CRF is unwired in the reference and the watershed is not in it"},
+        "roofline": {"bound": "hbm", "achieved": round(b * POST_BYTES_PER_IMAGE / (chain_ms * 1e-3) / 1e9, 1) if chain_ms else None,
+                     "peak": peak_hbm, "unit": "GB/s",
+                     "frac": round(b * POST_BYTES_PER_IMAGE / (chain_ms * 1e-3) / 1e9 / peak_hbm, 4) if chain_ms else None,
+                     "traffic": None, "peak_source": peak_src,
+                     "what": "reference post-processing chain of one batch: 1.44 MB/image algorithmic (SURVEY.md 8d) / its "
+                             "device time; per-kernel DRAM bytes and durations: profiles/r02_postproc_ncu.md"},
+    }
+    plan = net.module.plan(b, s, s, False) if hasattr(net, "module") else net.plan(b, s, s, False)
+    line["gpu_launches"] = (plan.launches_fwd + 40) * args.steps
+    if not args.no_cpu_baseline and world == 1:
+        cb = infer_cpu_baseline(args)
+        line["cpu_baseline"] = cb
+    return line
+
+
+def infer_cpu_baseline(args, n_fwd=2, n_post=8):
+    """the reference's CPU path for configs[3] on a bounded sample: eval forward (oracle port, fp32, all host threads) on
+    n_fwd tiles + the serial per-image post-processing chain (src/utils.py:352-355 loop over src/postprocessing.py
+    functions, restated in oracle/post_oracle.py) on n_post tiles, single process like the reference runs it; dense CRF and
+    watershed are the builder's restatements (parity unpinned) timed on one tile each"""
+    import numpy as np
+    import torch
+    from oracle import post_oracle as P, unet_oracle as O
+    import bench_data as synthetic
+    cores = usable_cores()
+    torch.set_num_threads(cores)
+    s = args.size
+    sd = O.make_reference_like_state_dict(args.encoder, seed=1234)
+    x, _ = synthetic.train_batch(n_fwd, s, seed=1234)
+    net = O.UNetOracle(sd, args.encoder)
+    with torch.no_grad():
+        net.forward(torch.from_numpy(x[:1]))
+        t0 = time.time()
+        net.forward(torch.from_numpy(x))
+        t_fwd = (time.time() - t0) / n_fwd
+    probs = synthetic.probability_maps(n_post, s, seed=7)
+    t0 = time.time()
+    for p_ in probs:
+        r = P.resize_image(P.crop_image_center_per_class(p_, 300, 300) if s == 320 else p_, (300, 300))
+        m_ = P.categorize_multilayer_image(r)
+        m_ = P.erode_image(m_, 2)
+        l_ = P.label_multilayer_image(m_)
+        l_ = P.dilate_image(l_, 2)
+        P.build_score(l_, r)
+    t_chain = (time.time() - t0) / n_post
+    extra = {}
+    try:
+        p1 = P.crop_image_center_per_class(probs[0], 300, 300) if s == 320 else P.resize_image(probs[0], (300, 300)).astype(np.float32)
+        img = np.random.RandomState(0).randn(3, 300, 300).astype(np.float32)
+        t0 = time.time()
+        P.dense_crf(img, p1.astype(np.float32))
+        extra["dense_crf_s_per_image"] = round(time.time() - t0, 3)
+    except Exception as e:
+        extra["dense_crf_error"] = str(e)
+    per_img = t_fwd + t_chain
+    return {"value": round(1.0 / per_img, 3), "unit": "tiles/s", "cores": cores, "kind": "port",
+            "sample": "oracle port: eval forward on %d tiles (%.2f s/tile, %d threads) + serial reference post-processing chain "
+                      "on %d tiles (%.1f ms/tile, 1 process); CRF / watershed excluded from `value` (unwired / absent in "
+                      "the reference)" % (n_fwd, t_fwd, cores, n_post, t_chain * 1e3),
+            "forward_s_per_tile": round(t_fwd, 3), "postproc_ms_per_tile": round(t_chain * 1e3, 2), **extra}
+
+
+def infer_reference_line(args):
+    cb = infer_cpu_baseline(args)
+    return {"impl": "reference", "metric": INFER_METRIC, "value": cb["value"], "unit": "tiles/s", "n_gpus": args.gpus,
+            "steps": 1, "warmup": 1, "requested": {"steps": args.steps, "warmup": args.warmup},
+            "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": infer_workload_name(args), "global_batch": args.batch * args.gpus, "parallelism": "cpu"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
 _REAL_STDOUT = None
 
 
@@ -203,14 +483,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_cudnn"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--encoder", type=int, default=101)
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--size", type=int, default=320)
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.batch is None:
+        args.batch = 64 if args.workload == "infer" else 32
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,12 +505,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if args.workload == "infer":
+            emit(infer_reference_line(args))
+            return
         cb = cpu_reference_arm(args)
+        # `steps` / `warmup` are what this arm RAN (each step = one reference train step on a bounded sample of the
+        # workload: batch `batch_run` instead of args.batch, so that the run ends within minutes on host cores);
+        # the values asked for on the command line are kept under `requested`
         line = {"impl": "reference", "metric": "300x300 tiles/sec fwd+bwd ResNet101-UNet", "value": cb["value"],
-                "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "unit": "tiles/s", "n_gpus": args.gpus, "steps": cb["steps_run"], "warmup": cb["warmup_run"],
+                "requested": {"steps": args.steps, "warmup": args.warmup, "batch": args.batch},
                 "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "global_batch": args.batch * args.gpus, "parallelism": "cpu"},
+                "config": {"workload": workload, "global_batch": args.batch * args.gpus, "parallelism": "cpu",
+                           "sample_batch": cb["batch_run"]},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -240,11 +532,25 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    if args.impl == "torch_cudnn":
+        line = library_baseline_line(args, dev, rank, world, workload)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     import mcb200
     from mcb200.models import PyTorchUNetWeighted
-    from oracle import synthetic
+    import bench_data as synthetic
+    if args.workload == "infer":
+        line = infer_line(args, dev, rank, world)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    dev = torch.device("cuda", local_rank)
     t_start = time.time()
 
     def note(msg):
@@ -387,6 +693,14 @@ def main():
         line["roofline"]["gemm_family_tflops"] = round(gemm_fl / gemm_ms, 1) if gemm_ms else None
         line["roofline"]["gemm_family_share_of_step"] = round(gemm_ms / total, 4)
         line["roofline"]["gemm_family_algorithmic_bytes"] = int(sum((v["algo_gbs"] or 0) * v["ms"] * 1e6 for v in gemm))
+    if not args.no_library_baseline and world == 1:
+        # the stock-PyTorch (cuDNN) train step of the same net on the same GPU, measured right here: the library
+        # baseline this framework has to beat
+        del Xh, Th
+        lb = library_baseline(args, dev, Xd, Td, steps=min(args.steps, 10), warmup=3)
+        line["library_baseline"] = lb
+        line["library_baseline"]["ours_over_library"] = round(value / lb["value"], 3) if lb.get("value") else None
+        note("library baseline done")
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_arm(args, sample_batch=2, steps=2, warmup=1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

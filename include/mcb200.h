@@ -276,6 +276,54 @@ int mcb_dense_crf(const float* probs, const uint8_t* rgb, float* out, float* wor
 int mcb_watershed(const void* prob, int prob_is_f64, const int* markers, const uint8_t* mask, int* labels,
                   int* workspace, int planes, int h, int w, int levels, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Callers on either side of the per-pixel chain and categorize_image.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* categorize_image (src/postprocessing.py:64-74) -> np.argmax(image, axis=0): prob fp32|fp64 [n][c][h][w] -> int64
+ * [n][h][w]; first maximum, NaN counts as the maximum (numpy semantics) */
+int mcb_argmax_channels(const void* prob, int prob_is_f64, long long* out, int n, int c, int h, int w, void* stream);
+
+/* test_time_augmentation_transform (src/loaders.py:470-480) for nv (image, variant) pairs: out[v] =
+ * rot90(flip(x[img_of[v]]), k); code[v] = k | flip << 2 (k quarter turns counter-clockwise; flip 0 none, 1 up-down,
+ * 2 left-right).  x fp32 [n][c][h][w], out fp32 [nv][c][h][w] (h == w when k is odd) */
+int mcb_tta_transform(const float* x, float* out, const int* img_of, const int* code, int nv, int c, int h, int w,
+                      void* stream);
+/* TestTimeAugmentationAggregator.transform + test_time_augmentation_inverse_transform (src/loaders.py:437-497) in one
+ * pass: out[i] = agg over the variants v of image i of flip(rot90(pred[v], -k)); pred fp32 [nv][c][h][w] holds class
+ * probabilities, or logits when from_logits (the class softmax of src/models.py:88-92 is then taken in registers).
+ * var_start int32 [n+1], var_index int32 [nv]; method 0 gmean, 1 mean, 2 max, 3 min; out fp32 [n][c][h][w]; c <= 8 */
+int mcb_tta_aggregate(const float* pred, int from_logits, const int* var_start, const int* var_index, const int* code,
+                      float* out, int n, int c, int h, int w, int method, void* stream);
+
+/* Instance emission (src/utils.py:61-127; src/postprocessing.py:284-352).  An instance is (plane, label); its slot is
+ * offsets[plane] + label - 1 with offsets the exclusive prefix of counts (labels per plane, from mcb_ccl_label).
+ * geometry: geo int32 [total][5] = {area, rmin, rmax, cmin, cmax} (caller initialises {0, INT_MAX, -1, INT_MAX, -1});
+ * with prob (fp32|fp64 planes aligned with labels): psum fp64 [total] (zeroed) and pmax int32 [total] (order-preserving
+ * integer image of the fp32 maximum, initialised to that of -inf) */
+int mcb_instance_geometry(const int* labels, const void* prob, int prob_is_f64, const int* offsets, const int* counts,
+                          int* geo, double* psum, int* pmax, int planes, int h, int w, void* stream);
+/* COCO run-length encoding of every instance mask (pycocotools rleEncode on the Fortran-ordered mask,
+ * src/utils.py:118-120): pass write=0 fills nchanges[slot] = number of value changes of the column-major scan; the
+ * caller prefix-sums it into out_start; pass write=1 stores the change positions at changes[out_start[slot]...] and
+ * spans[slot] = 1 when a run of ones covers several columns (rleToBbox then reports the full height).
+ * inst_plane int32 [total] = plane of each slot */
+int mcb_rle_walk(const int* labels, const int* offsets, const int* counts, const int* geo, const int* inst_plane,
+                 const int* out_start, int* nchanges, int* changes, int* spans, int total, int h, int w, int write,
+                 void* stream);
+/* run lengths from change positions: instance `slot` owns counts [out_start[slot] + slot, +nchanges[slot] + 1);
+ * slot_of_count int32 [total_counts]; cnts uint32 [total_counts] */
+int mcb_rle_counts(const int* changes, const int* nchanges, const int* out_start, const int* slot_of_count,
+                   uint32_t* cnts, long total_counts, int hw, void* stream);
+/* intersection pixel counts between the instances of two label planes of one image (the IoU matrix of
+ * remove_overlapping_masks, src/postprocessing.py:355-386): inter int32 [ka][kb], zeroed by the caller */
+int mcb_pair_intersections(const int* labels_a, const int* labels_b, int* inter, int ka, int kb, int h, int w,
+                           void* stream);
+/* get_contour_length (src/postprocessing.py:340-352): mask pixels with a 4-neighbour outside the mask, per instance;
+ * clen int32 [total], zeroed by the caller */
+int mcb_contour_length(const int* labels, const int* offsets, const int* counts, int* clen, int planes, int h, int w,
+                       void* stream);
+
 /* hardware probe used while designing the haloed 3x3 path (debug only, see csrc/probe.cu) */
 int mcb_debug_umma_probe(const void* a, const void* ident, float* out, int rows, int rowb, int shift, int sbo,
                          int base_off_mode, void* stream);

@@ -160,3 +160,17 @@ lib.mcb_bn_eval_params_batched.restype = ci
 
 lib.mcb_instance_scores_strided.argtypes = [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, vp]
 lib.mcb_instance_scores_strided.restype = ci
+
+_SIGS4 = {
+    "mcb_argmax_channels": [vp, ci, vp, ci, ci, ci, ci, vp],
+    "mcb_tta_transform": [vp, vp, vp, vp, ci, ci, ci, ci, vp],
+    "mcb_tta_aggregate": [vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
+    "mcb_instance_geometry": [vp, vp, ci, vp, vp, vp, vp, vp, ci, ci, ci, vp],
+    "mcb_rle_walk": [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp],
+    "mcb_rle_counts": [vp, vp, vp, vp, vp, cl, ci, vp],
+    "mcb_pair_intersections": [vp, vp, vp, ci, ci, ci, ci, vp],
+    "mcb_contour_length": [vp, vp, vp, vp, ci, ci, ci, vp],
+}
+for _n, _a in _SIGS4.items():
+    getattr(lib, _n).argtypes = _a
+    getattr(lib, _n).restype = ci

@@ -12,6 +12,7 @@ arena are all-reduced over NCCL.  Nothing here computes on the CPU."""
 import math
 import os
 import shutil
+import warnings
 from functools import partial
 
 import numpy as np
@@ -43,6 +44,10 @@ PRETRAINED_NETWORKS = {
 # losses (autograd-compatible wrappers over the two-phase CUDA kernels)
 # ---------------------------------------------------------------------------------------------------------------------
 class _FusedLoss(torch.autograd.Function):
+    """loss of the LOCAL batch (what the reference's validation callbacks expect from `loss_function(outputs, target)`,
+    src/steps/pytorch/validation.py:47-80, possibly on one rank only); the cross-rank Dice / CE sums of multi-GPU
+    training are all-reduced by FusedTrainStep, never here (pass sync=True in cfg to opt in)."""
+
     @staticmethod
     def forward(ctx, logits, target, mode, cfg):
         logits = logits.contiguous().float()
@@ -50,7 +55,7 @@ class _FusedLoss(torch.autograd.Function):
         sums = torch.zeros(4, dtype=torch.float64, device=logits.device)
         ops.loss_partials(logits, target, sums, mode=mode, **cfg)
         world = 1
-        if cfg.get("sync", True) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if cfg.get("sync", False) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(sums)
             world = dist.get_world_size()
         dlogits = torch.empty_like(logits)
@@ -103,6 +108,25 @@ class NullCallbacks:
     def training_break(self, *a, **k): return False
 
 
+def callbacks_unet(callbacks_config):
+    """src/models.py:295-307: the reference builds its CallbackList (timing, training / validation monitors, checkpoint,
+    exponential LR schedule, early stopping, neptune) from `callbacks_config` in the transformer's constructor
+    (src/models.py:60).  Those callbacks are host-side bookkeeping of the reference package and plug in unchanged, so
+    they are taken from it when it is importable (i.e. whenever this transformer runs inside the reference's pipeline);
+    outside the reference tree there is nothing to build them from, which is said loudly, not silently."""
+    if not callbacks_config:
+        return NullCallbacks()
+    try:
+        from src.models import callbacks_unet as reference_callbacks_unet
+    except Exception as e:  # reference package (or one of its dependencies) not importable
+        warnings.warn("mcb200: callbacks_config given but the reference package `src` is not importable (%s: %s); "
+                      "training runs WITHOUT checkpointing / validation / LR schedule / early stopping. Pass "
+                      "`callbacks=` explicitly or run inside the reference tree." % (type(e).__name__, e),
+                      RuntimeWarning, stacklevel=3)
+        return NullCallbacks()
+    return reference_callbacks_unet(callbacks_config)
+
+
 def weight_regularization_unet(model, regularize, weight_decay_conv2d):
     """src/models.py:287-292"""
     if regularize:
@@ -122,7 +146,9 @@ class Model:
         self.loss_function = None
         self.callbacks = None
         self.validation_loss = {}
-        self._fused = None
+        self._fused = None          # the FusedTrainStep of the most recent batch shape
+        self._fused_cache = {}      # (X.shape, target.shape) -> FusedTrainStep (the last batch of an epoch is smaller)
+        self._opt_state = None      # Adam moments + step count, arena-sized, shared by every cached step
         self._step = 0
 
     @property
@@ -143,6 +169,12 @@ class Model:
     def fit(self, datagen, validation_datagen=None, meta_valid=None):
         self._initialize_model_weights()
         self._to_device()
+        if not isinstance(self.model, nn.DataParallel):
+            # src/models.py:65: the reference wraps the net, so callbacks see `transformer.model` as a DataParallel and
+            # ModelCheckpoint writes `module.`-prefixed keys.  One process drives one GPU here: the wrapper has a single
+            # device and forwards straight to the module.
+            dev = self._net()._p32.device
+            self.model = nn.DataParallel(self.model, device_ids=[dev.index if dev.index is not None else 0])
         self.callbacks.set_params(self, validation_datagen=validation_datagen, meta_valid=meta_valid)
         self.callbacks.on_train_begin()
         batch_gen, steps = datagen
@@ -196,12 +228,29 @@ class Model:
             batch_loss.backward()
             self.optimizer.step()
             return {'sum': batch_loss.detach()}
-        if self._fused is None or self._fused.key != (tuple(X.shape), tuple(target.shape)):
-            self._fused = FusedTrainStep(net, X.shape, target.shape, spec[0], spec[1])
+        self._fused = self._fused_step(net, X.shape, target.shape, spec)
         group = self.optimizer.param_groups[0]
         loss = self._fused.step(X, target, lr=group['lr'], betas=group.get('betas', (0.9, 0.999)),
                                 eps=group.get('eps', 1e-8), weight_decay=group.get('weight_decay', 0.0))
         return {'sum': loss}
+
+    def _fused_step(self, net, x_shape, t_shape, spec):
+        """the captured train step for this batch shape.  Adam's moments and step count live on the transformer, not in
+        the captured step: a partial last batch (the reference's DataLoader has no drop_last, src/loaders.py:220) or a
+        device round trip of the model (ModelCheckpoint -> save_model: model.cpu(); save; model.cuda()) re-captures
+        graphs but never resets the optimizer."""
+        gen = net._generation
+        st = self._opt_state
+        if st is None:
+            st = self._opt_state = AdamState(net)
+        elif st.generation != gen or st.m.device != net._p32.device or st.m.numel() != net._p32.numel():
+            st.rebind(net)              # arenas were re-created: carry m / v / t over, drop steps that baked pointers in
+            self._fused_cache = {}
+        key = (tuple(x_shape), tuple(t_shape))
+        fused = self._fused_cache.get(key)
+        if fused is None:
+            fused = self._fused_cache[key] = FusedTrainStep(net, x_shape, t_shape, spec[0], spec[1], st)
+        return fused
 
     # ---- inference (src/steps/pytorch/models.py:115-142)
     def _transform(self, datagen, validation_datagen=None):
@@ -230,6 +279,7 @@ class Model:
         net.load_state_dict(sd)
         if torch.cuda.is_available():
             self._to_device()
+            net.refresh_operands()   # the captured steps read the bf16 operand copy, which only Adam refreshes
         return self
 
     def save(self, filepath):
@@ -254,7 +304,7 @@ class BasePyTorchUNet(Model):
         self.optimizer = optim.Adam(self.weight_regularization(self.model, **architecture_config['regularizer_params']),
                                     **architecture_config['optimizer_params'])
         self.loss_function = None
-        self.callbacks = callbacks if callbacks is not None else NullCallbacks()
+        self.callbacks = callbacks if callbacks is not None else callbacks_unet(self.callbacks_config)
 
     def transform(self, datagen, validation_datagen=None, *args, **kwargs):
         """src/models.py:88-92: logits -> softmax probabilities, as numpy like the reference"""
@@ -332,6 +382,23 @@ class PyTorchUNetWeightedStream(_StreamMixin, PyTorchUNetWeighted):
 # ---------------------------------------------------------------------------------------------------------------------
 # fused train step
 # ---------------------------------------------------------------------------------------------------------------------
+class AdamState:
+    """Adam's first / second moments (fp32, laid out like the master arena) and its step count"""
+
+    def __init__(self, net):
+        self.m = torch.zeros_like(net._p32)
+        self.v = torch.zeros_like(net._p32)
+        self.t = 0
+        self.generation = net._generation
+
+    def rebind(self, net):
+        if self.m.numel() != net._p32.numel():
+            raise RuntimeError("the parameter arena changed size; the optimizer state cannot be carried over")
+        self.m = self.m.to(net._p32.device)
+        self.v = self.v.to(net._p32.device)
+        self.generation = net._generation
+
+
 class FusedTrainStep:
     """forward plan -> loss partials -> [all-reduce sums] -> loss gradient -> backward plan -> [all-reduce grads] ->
     fused Adam (+ bf16 operand refresh), as CUDA graph segments on the current stream.
@@ -340,8 +407,9 @@ class FusedTrainStep:
     BatchNorm (per-replica batch statistics, src/models.py:65) while the loss is global-batch (Dice sums all-reduced,
     CE mean over the global pixel count) and gradients are summed; see DESIGN.md (multi-GPU)."""
 
-    def __init__(self, net, x_shape, t_shape, loss_mode, loss_cfg):
+    def __init__(self, net, x_shape, t_shape, loss_mode, loss_cfg, opt_state=None):
         self.net = net
+        self.opt = opt_state if opt_state is not None else AdamState(net)
         self.key = (tuple(x_shape), tuple(t_shape))
         n, _, h, w = x_shape
         self.plan = net.plan(n, h, w, True)
@@ -351,9 +419,6 @@ class FusedTrainStep:
         self.target = torch.zeros(t_shape, dtype=torch.float32, device=dev)
         self.sums = torch.zeros(4, dtype=torch.float64, device=dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        self.m = torch.zeros_like(net._p32)
-        self.v = torch.zeros_like(net._p32)
-        self.t = 0
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.graphs = None
         self.pixels = n * h * w
@@ -400,7 +465,7 @@ class FusedTrainStep:
                 betas, eps, wd = self._adam_cfg
 
                 def upd(lo, hi):
-                    return lambda: ops.adam_step_dyn(net._p32[lo:hi], net._g32[lo:hi], self.m[lo:hi], self.v[lo:hi],
+                    return lambda: ops.adam_step_dyn(net._p32[lo:hi], net._g32[lo:hi], self.opt.m[lo:hi], self.opt.v[lo:hi],
                                                      net._w16[lo:hi], self._hyper, betas, eps, wd, 1.0)
                 hooks = {last: upd(lo, hi) for _, last, lo, hi in self.plan.bwd_segments()}
             works = []
@@ -420,7 +485,7 @@ class FusedTrainStep:
 
     def _adam(self, lr, betas, eps, weight_decay):
         net = self.net
-        ops.adam_step(net._p32, net._g32, self.m, self.v, net._w16, self.t, lr, betas, eps, weight_decay, 1.0)
+        ops.adam_step(net._p32, net._g32, self.opt.m, self.opt.v, net._w16, self.opt.t, lr, betas, eps, weight_decay, 1.0)
 
     def _capture(self):
         segs = [self._seg_forward]
@@ -471,18 +536,19 @@ class FusedTrainStep:
 
     def step(self, X, target, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         finish_target = self._stage_inputs(X, target)
-        self.t += 1
+        self.opt.t += 1
+        t = self.opt.t
         if self.adam_in_graph:
             cfg = (tuple(betas), eps, weight_decay)
             if self._adam_cfg is None:
                 self._adam_cfg = cfg
             elif self._adam_cfg != cfg:   # baked into the captured launches
                 raise RuntimeError("Adam betas / eps / weight_decay changed after the train step was captured")
-            host, ev = self._hyper_ring[self.t % len(self._hyper_ring)]
+            host, ev = self._hyper_ring[t % len(self._hyper_ring)]
             ev.synchronize()
             host[0] = lr
-            host[1] = 1.0 - betas[0] ** self.t
-            host[2] = (1.0 - betas[1] ** self.t) ** 0.5
+            host[1] = 1.0 - betas[0] ** t
+            host[2] = (1.0 - betas[1] ** t) ** 0.5
             self._hyper.copy_(host, non_blocking=True)
             ev.record()
         first = self.graphs is None and self.use_graphs
@@ -531,7 +597,8 @@ class FusedTrainStep:
         if first:
             torch.cuda.synchronize()
             self._capture()
-        return self.loss.clone()
+        # shape (1,): the reference's callbacks read `loss.data.cpu().numpy()[0]` (src/steps/pytorch/callbacks.py:134)
+        return self.loss.reshape(1).clone()
 
     def count_launches(self):
         """kernel launches of one step (our kernels + memsets issued by the plan)"""

@@ -167,9 +167,22 @@ def resize_image(image, target_size):
     return resize_batch(x[None], target_size)[0].cpu().numpy()
 
 
+def categorize_batch(probs):
+    """probs (N, C, H, W) float32|float64 cuda -> (N, H, W) int64 cuda: np.argmax over the channel axis"""
+    assert probs.is_cuda and probs.dtype in (torch.float32, torch.float64)
+    probs = probs.contiguous()
+    n, c, h, w = probs.shape
+    out = torch.empty((n, h, w), dtype=torch.int64, device=probs.device)
+    L.fcall("mcb_argmax_channels", probs.data_ptr(), int(probs.dtype == torch.float64), out.data_ptr(), n, c, h, w)
+    return out
+
+
 def categorize_image(image):
-    raise NotImplementedError("categorize_image (argmax) is only used by the validation callback; use "
-                              "categorize_multilayer_image")
+    """src/postprocessing.py:64-74: np.argmax(image, axis=0) (the validation callback's categoriser,
+    src/callbacks.py:168-200); (C, H, W) -> (H, W) int64"""
+    image = np.asarray(image)
+    x = _to_dev(image, torch.float64 if image.dtype == np.float64 else torch.float32)
+    return categorize_batch(x[None])[0].cpu().numpy()
 
 
 def categorize_multilayer_image(image):
@@ -283,6 +296,136 @@ def crop_image_center_per_class(image, h_crop, w_crop):
         h_start, w_start = int((h - h_crop) / 2.), int((w - w_crop) / 2.)
         out.append(class_prediction[h_start:-h_start, w_start:-w_start])
     return np.stack(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# instance level: non-maximum suppression and scoring-model features (src/postprocessing.py:18-45, 261-386)
+# ---------------------------------------------------------------------------------------------------------------------
+def pair_intersections(labels_a, labels_b, ka, kb):
+    """labels_a / labels_b (H, W) int32 cuda, ka / kb their label counts -> (ka, kb) int32 cuda intersection areas"""
+    assert labels_a.is_cuda and labels_a.dtype == torch.int32 and labels_a.shape == labels_b.shape
+    h, w = labels_a.shape
+    inter = torch.zeros((max(ka, 1), max(kb, 1)), dtype=torch.int32, device=labels_a.device)
+    L.fcall("mcb_pair_intersections", labels_a.contiguous().data_ptr(), labels_b.contiguous().data_ptr(),
+            inter.data_ptr(), int(ka), int(kb), h, w)
+    return inter[:ka, :kb]
+
+
+def remove_overlapping_masks(image, scores, iou_threshold=0.5):
+    """src/postprocessing.py:355-379: instances of all layers sorted by score; an instance whose IoU with a better one
+    exceeds the threshold has its score set to 0 (its mask stays).  The reference builds two full-image masks for
+    every pair; here areas and the layer-pair intersection tables come from two device passes and the greedy sweep
+    runs on the resulting small integer matrices."""
+    from . import utils as U
+    lab = _to_dev(np.asarray(image).astype(np.int32), torch.int32)
+    n_layers = lab.shape[0]
+    counts = lab.reshape(n_layers, -1).max(dim=1).values.to(torch.int32)
+    geo = U.instance_geometry(lab, counts)
+    k = geo["counts"]
+    inter = {}
+    for a in range(n_layers):
+        for b in range(a + 1, n_layers):
+            if k[a] and k[b]:
+                inter[(a, b)] = pair_intersections(lab[a], lab[b], int(k[a]), int(k[b])).cpu().numpy()
+
+    def area(layer, label):
+        return int(geo["area"][geo["offsets"][layer] + label - 1]) if label <= k[layer] else 0
+
+    def iou(i, j):
+        (la, a), (lb, b) = i, j
+        if la == lb:
+            inter_ab = area(la, a) if a == b else 0
+        elif a > k[la] or b > k[lb]:
+            inter_ab = 0
+        else:
+            inter_ab = int(inter[(la, lb)][a - 1, b - 1]) if la < lb else int(inter[(lb, la)][b - 1, a - 1])
+        union = area(la, a) + area(lb, b) - inter_ab
+        return inter_ab / union if union else float("nan")
+
+    scores_with_labels = []
+    for layer_nr, layer_scores in enumerate(scores):
+        scores_with_labels.extend([(score, layer_nr, label_nr + 1) for label_nr, score in enumerate(layer_scores)])
+    scores_with_labels.sort(key=lambda x: x[0], reverse=True)
+    i = 0
+    while i < len(scores_with_labels):          # the reference mutates the list it iterates; same visiting order
+        score_i, layer_nr_i, label_nr_i = scores_with_labels[i]
+        for score_j, layer_nr_j, label_nr_j in list(scores_with_labels[i + 1:]):
+            if iou((layer_nr_i, label_nr_i), (layer_nr_j, label_nr_j)) > iou_threshold:
+                scores_with_labels.remove((score_j, layer_nr_j, label_nr_j))
+                scores[layer_nr_j][label_nr_j - 1] = 0
+        i += 1
+    return image, scores
+
+
+class NonMaximumSupression:
+    """src/postprocessing.py:34-45"""
+
+    def __init__(self, iou_threshold, num_threads=1):
+        self.iou_threshold = iou_threshold
+        self.num_threads = num_threads
+
+    def fit(self, *args, **kwargs):
+        return self
+
+    def fit_transform(self, *args, **kwargs):
+        return self.transform(*args, **kwargs)
+
+    def load(self, filepath):
+        return self
+
+    def save(self, filepath):
+        import joblib
+        joblib.dump({}, filepath)
+
+    def transform(self, images_with_scores):
+        return {'images_with_scores': [remove_overlapping_masks(*p, iou_threshold=self.iou_threshold)
+                                       for p in images_with_scores]}
+
+
+def get_thresholds(category_layers=None):
+    """src/postprocessing.py:321-327"""
+    return layer_thresholds(category_layers)[0]
+
+
+def instance_features(labels, probabilities, category_layers=None):
+    """get_features_for_image without ground truth (src/postprocessing.py:261-306): per layer a list of per-instance
+    feature dicts {iou: None, threshold, area, mean_prob, max_prob, bbox_ar, bbox_area, bbox_fill, min_dist_to_border,
+    max_dist_to_border, contour_length}.  labels (L, H, W) int32, probabilities (C, H, W)."""
+    from . import utils as U
+    category_layers = CATEGORY_LAYERS if category_layers is None else category_layers
+    lab = _to_dev(np.asarray(labels).astype(np.int32), torch.int32)
+    n_layers, h, w = lab.shape
+    inds = np.cumsum(category_layers)
+    probs = np.asarray(probabilities)
+    chan = [int(np.searchsorted(inds, li, side='right')) for li in range(n_layers)]
+    pr = _to_dev(probs[chan], torch.float64 if probs.dtype == np.float64 else torch.float32)
+    counts = lab.reshape(n_layers, -1).max(dim=1).values.to(torch.int32)
+    geo = U.instance_geometry(lab, counts, pr)
+    total = int(geo["counts"].sum())
+    clen = torch.zeros(max(total, 1), dtype=torch.int32, device=lab.device)
+    if total:
+        L.fcall("mcb_contour_length", lab.data_ptr(), geo["_offsets"].data_ptr(), geo["_counts"].data_ptr(),
+                clen.data_ptr(), n_layers, h, w)
+    clen = clen.cpu().numpy()
+    thresholds = get_thresholds(category_layers)
+    out = []
+    for li in range(n_layers):
+        feats = []
+        for i in range(int(geo["counts"][li])):
+            s = int(geo["offsets"][li]) + i
+            area = int(geo["area"][s])
+            bbox = (int(geo["rmin"][s]), int(geo["rmax"][s]) + 1, int(geo["cmin"][s]), int(geo["cmax"][s]) + 1)
+            bh, bw = bbox[1] - bbox[0], bbox[3] - bbox[2]
+            dists = (bbox[0], h - bbox[1], bbox[2], w - bbox[3])
+            feats.append({'iou': None, 'threshold': round(thresholds[li], 2), 'area': area,
+                          'mean_prob': float(geo["psum"][s]) / area,
+                          # np.where(mask, probabilities, 0).max(): the zeros outside the mask take part
+                          'max_prob': max(float(geo["pmax"][s]), 0.0) if area < h * w else float(geo["pmax"][s]),
+                          'bbox_ar': bh / bw, 'bbox_area': bw * bh, 'bbox_fill': area / (bw * bh),
+                          'min_dist_to_border': min(dists), 'max_dist_to_border': max(dists),
+                          'contour_length': int(clen[s])})
+        out.append(feats)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

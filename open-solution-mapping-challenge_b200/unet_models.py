@@ -94,7 +94,8 @@ class UNetResNet(nn.Module):
         self._slots = {}
         self._plans = {}
         self._p32 = self._g32 = self._w16 = None
-        self._build_arenas()
+        self._generation = 0   # bumped whenever the arenas are re-created (device move): plans, CUDA graphs and fused
+        self._build_arenas()   # train steps that baked the old pointers in are stale from then on
 
     # ------------------------------------------------------------------------------------------------ arenas
     def _arena_params(self):
@@ -130,7 +131,18 @@ class UNetResNet(nn.Module):
         self._slots, self._p32, self._g32 = slots, p32, g32
         self._w16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self._plans = {}
-        self._adam = None
+        self._generation += 1
+
+    def _params_alias_arena(self):
+        """every arena parameter still is a view of the current master arena (no .to()/.cpu() moved it away)"""
+        if self._p32 is None:
+            return False
+        base, dev = self._p32.data_ptr(), self._p32.device
+        for _, p, _ in self._arena_params():
+            s = self._slots.get(id(p))
+            if s is None or p.device != dev or p.dtype != torch.float32 or p.data_ptr() != base + 4 * s.off:
+                return False
+        return True
 
     @staticmethod
     def _view(arena, s):
@@ -144,8 +156,13 @@ class UNetResNet(nn.Module):
         return flat.view(s.shape)
 
     def _apply(self, fn, *args, **kwargs):
+        """.cuda() / .cpu() / .to(): nn.Module moves each parameter's data separately, which tears the views off the
+        arena -- re-pack them into fresh arenas on the new device.  A call that moves nothing (`.cuda()` on a model that
+        already lives there: the reference's save_model does model.cpu(); save; model.cuda() every checkpoint,
+        src/steps/pytorch/utils.py:67-75, and `_to_device` runs every batch) keeps arenas, plans and graphs."""
         super()._apply(fn, *args, **kwargs)
-        self._build_arenas()
+        if not self._params_alias_arena():
+            self._build_arenas()
         return self
 
     def state_dict(self, *args, **kwargs):

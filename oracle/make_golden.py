@@ -82,9 +82,106 @@ def golden_unet(um, mo):
     print("unet.npz", {k: v.shape for k, v in rec.items() if v.ndim == 0 or "logits" in k})
 
 
+from oracle.make_golden_cases import CONFIG_CASES, CONFIG_GRAD_KEYS, GRAD_HEAD, LOGIT_STRIDE  # noqa: E402
+
+
+def golden_unet_configs(um, mo):
+    """reference logits (eval + train), loss and a spread of gradients at the BASELINE.json configurations.  Inputs
+    and the initial weights are NOT stored: both sides regenerate them from the seed (synthetic.train_batch(n, s, 1234),
+    unet_oracle.make_reference_like_state_dict(depth, seed=1234), which test_oracle_pins pins to the reference's own
+    initialisation)."""
+    rec = {}
+    for tag, enc, depth, n, s in CONFIG_CASES:
+        cfg = ref_shim.reference_unet_config(enc, image_hw=(256, 256))
+        torch.manual_seed(1234)
+        model = mo.PyTorchUNetWeighted(**cfg)
+        x, t = synthetic.train_batch(n, s, seed=1234)
+        X, T = torch.from_numpy(x), torch.from_numpy(t)
+        model.model.eval()
+        with torch.no_grad():
+            rec["eval_logits_" + tag] = model.model(X[:1]).numpy()   # eval mode is per image: image 0 is enough
+        model.model.train()
+        out = model.model(X)
+        name, loss_fn, weight = model.loss_function[0]
+        loss = loss_fn(out, T) * weight
+        loss.backward()
+        rec["train_logits_" + tag] = out.detach().numpy()
+        rec["loss_" + tag] = np.array(float(loss))
+        sd = dict(model.model.named_parameters())
+        for k in CONFIG_GRAD_KEYS:
+            rec["grad_%s_%s" % (tag, k)] = sd[k].grad.detach().numpy().reshape(-1)[:GRAD_HEAD].copy()
+        print(tag, "loss", float(loss), "logit range", float(out.min()), float(out.max()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "unet_configs.npz"), **rec)
+    print("unet_configs.npz", os.path.getsize(os.path.join(OUT, "unet_configs.npz")) >> 10, "KiB")
+
+
+def golden_unet_conditioned(um, mo):
+    """the same configurations on the conditioned checkpoint (damped residual branches, calibrated running statistics):
+    the regime of a trained net, where logits AND deep-encoder gradients are reproducible quantities.  The checkpoint
+    is regenerated from the seed on both sides (oracle.unet_oracle.conditioned_state_dict); here it is loaded into the
+    UNMODIFIED reference network, whose own calibration pass must reproduce the checkpoint's running statistics."""
+    from oracle import unet_oracle as O
+    rec = {}
+    s3 = LOGIT_STRIDE
+    for tag, enc, depth, n, s in CONFIG_CASES:
+        x, t = synthetic.train_batch(n, s, seed=1234)
+        X, T = torch.from_numpy(x), torch.from_numpy(t)
+        sd = O.conditioned_state_dict(depth, X, seed=1234)
+        cfg = ref_shim.reference_unet_config(enc, image_hw=(256, 256))
+        model = mo.PyTorchUNetWeighted(**cfg)
+        net = model.model
+        raw = O.make_reference_like_state_dict(depth, seed=1234)
+        last = "bn2" if depth == 34 else "bn3"
+        for k in raw:   # damp, then let the reference calibrate itself (momentum 1): must equal the oracle's checkpoint
+            if k.startswith("encoder.layer") and k.endswith("." + last + ".weight"):
+                raw[k] = raw[k] * 0.25
+        for k in list(raw):
+            for new, old in (("conv2.", "encoder.layer1."), ("conv3.", "encoder.layer2."), ("conv4.", "encoder.layer3."),
+                             ("conv5.", "encoder.layer4.")):
+                if k.startswith(new):
+                    raw[k] = raw[old + k[len(new):]]
+        net.load_state_dict(raw)
+        bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+        for m in bns:
+            m.momentum = 1.0
+        net.train()
+        with torch.no_grad():
+            net(X)
+        for m in bns:
+            m.momentum = 0.1
+        got = net.state_dict()
+        for k, v in sd.items():
+            if v.is_floating_point():
+                assert torch.equal(got[k], v), ("reference calibration differs from the oracle checkpoint", k)
+        net.eval()
+        with torch.no_grad():
+            rec["eval_logits_" + tag] = net(X[:1]).numpy()[:, :, ::s3, ::s3].copy()
+        net.train()
+        out = net(X)
+        name, loss_fn, weight = model.loss_function[0]
+        loss = loss_fn(out, T) * weight
+        loss.backward()
+        rec["train_logits_" + tag] = out.detach().numpy()[:, :, ::s3, ::s3].copy()
+        rec["loss_" + tag] = np.array(float(loss))
+        params = dict(net.named_parameters())
+        for k in CONFIG_GRAD_KEYS:
+            rec["grad_%s_%s" % (tag, k)] = params[k].grad.detach().numpy().reshape(-1)[:GRAD_HEAD].copy()
+        print(tag, "conditioned: loss", float(loss), "logit range", float(out.min()), float(out.max()),
+              "eval range", float(rec["eval_logits_" + tag].min()), float(rec["eval_logits_" + tag].max()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "unet_conditioned.npz"), **rec)
+    print("unet_conditioned.npz", os.path.getsize(os.path.join(OUT, "unet_conditioned.npz")) >> 10, "KiB")
+
+
 if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     os.makedirs(OUT, exist_ok=True)
     um, mo, pp, ut = ref_shim.reference_modules()
-    golden_postproc(pp, ut)
-    golden_unet(um, mo)
+    which = sys.argv[1:] or ["postproc", "unet", "configs", "conditioned"]
+    if "postproc" in which:
+        golden_postproc(pp, ut)
+    if "unet" in which:
+        golden_unet(um, mo)
+    if "configs" in which:
+        golden_unet_configs(um, mo)
+    if "conditioned" in which:
+        golden_unet_conditioned(um, mo)

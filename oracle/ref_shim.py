@@ -95,6 +95,7 @@ def install():
         yaml.load = _load
 
     from . import post_oracle as P
+    from . import instances_oracle as I
 
     _module("attrdict", AttrDict=_AttrDict)
     ext = _module("sklearn.externals", joblib=joblib)
@@ -111,7 +112,7 @@ def install():
     iaa = _module("imgaug.augmenters")
     ia.augmenters = iaa
     sk = _module("skimage")
-    sk.transform = _module("skimage.transform", resize=P.skimage_resize)
+    sk.transform = _module("skimage.transform", resize=P.skimage_resize, rotate=I.skimage_rotate)
     sk.morphology = _module("skimage.morphology", erosion=P.skimage_erosion, dilation=P.skimage_dilation,
                             rectangle=P.skimage_rectangle)
     pd = _module("pydensecrf")

@@ -70,6 +70,25 @@ def make_reference_like_state_dict(encoder_depth, num_classes=2, num_filters=32,
     return sd
 
 
+def conditioned_state_dict(encoder_depth, x, seed=1234, damp=0.25):
+    """A well-conditioned stand-in for a TRAINED checkpoint (none can be downloaded here): the seed's random init with
+    (1) the last BatchNorm scale of every residual block multiplied by `damp` -- residual branches of trained ResNets
+    are small next to the identity path; at the raw init 33-50 undamped blocks amplify any rounding difference until
+    deep gradients of two valid fp32 evaluations no longer correlate -- and (2) BatchNorm running statistics set to
+    the batch statistics of `x` (one train-mode pass with momentum 1), so eval mode normalises like train mode instead
+    of with the untouched (0, 1) buffers that make the raw-init net's eval activations explode."""
+    sd = make_reference_like_state_dict(encoder_depth, seed=seed)
+    last = "bn2" if encoder_depth == 34 else "bn3"
+    seen = set()
+    for k, v in sd.items():
+        if k.startswith("encoder.layer") and k.endswith("." + last + ".weight") and id(v) not in seen:
+            v.mul_(damp)       # the conv2..conv5 alias entries share these tensors
+            seen.add(id(v))
+    with torch.no_grad():
+        UNetOracle(sd, encoder_depth, update_running_stats=True, momentum=1.0).forward(x, training=True)
+    return sd
+
+
 class _RoundBF16(torch.autograd.Function):
     """bf16 storage point: value rounded in forward, gradient rounded in backward (the CUDA path stores both
     activations and activation gradients as bf16)"""
@@ -103,7 +122,8 @@ class UNetOracle:
     activations and activation gradients; fp32 accumulation, statistics, parameters and logits) so that the
     product can be compared at tight tolerance; emulate_bf16=False is the reference's fp32 arithmetic."""
 
-    def __init__(self, sd, encoder_depth, update_running_stats=True, emulate_bf16=False):
+    def __init__(self, sd, encoder_depth, update_running_stats=True, emulate_bf16=False, momentum=BN_MOMENTUM):
+        self.momentum = momentum
         self.sd = strip_module_prefix(sd)
         self.depth = encoder_depth
         self.kind, self.blocks = LAYERS[encoder_depth]
@@ -122,7 +142,7 @@ class UNetOracle:
         rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
         if training and not self.update:
             rm, rv = rm.clone(), rv.clone()
-        y = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training, BN_MOMENTUM, BN_EPS)
+        y = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training, self.momentum, BN_EPS)
         if training and self.update and (prefix + ".num_batches_tracked") in sd:
             sd[prefix + ".num_batches_tracked"] += 1
         return y

@@ -135,3 +135,20 @@ def test_live_against_reference_code():
         want = ref(x)
         got = O.UNetOracle(sd, 34).forward(x, training=False)
     assert torch.equal(want, got)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_unet_oracle_matches_config_goldens(case):
+    """tests/golden/unet_configs.npz (BASELINE.json configs 1 / 2 / 5: R34 b2 @256, R101 @320, R152 @512) was produced by
+    the UNMODIFIED reference from seed 1234; the seed-regenerated weights + inputs and the oracle network must reproduce
+    its eval logits (image 0), which pins both the fixture's inputs and the oracle at those depths / resolutions."""
+    from oracle.make_golden_cases import CONFIG_CASES
+    tag, enc, depth, n, s = CONFIG_CASES[case]
+    g = np.load(os.path.join(GOLD, "unet_configs.npz"))
+    sd = O.make_reference_like_state_dict(depth, seed=1234)
+    x, _ = synthetic.train_batch(n, s, seed=1234)
+    with torch.no_grad():
+        ev = O.UNetOracle(sd, depth).forward(torch.from_numpy(x[:1]), training=False)
+    ref = g["eval_logits_" + tag]
+    assert ev.shape == ref.shape
+    assert np.abs(ev.numpy() - ref).max() < 1e-6
