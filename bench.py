@@ -607,7 +607,7 @@ def main():
     # after it has enqueued step i+1 -- so the H2D copy of the next batch and the host-side launch work overlap compute.
     # (A plain loss.cpu() of the previous step would be stream-ordered behind the step just enqueued and stall the host
     # for a whole step: tools/dbg_e2e.py.)
-    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
     prev = {"i": 0, "pending": False}
 

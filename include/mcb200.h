@@ -31,6 +31,8 @@ extern "C" {
 
 const char* mcb_last_error(void);
 int mcb_version(void);
+/* zero-fill of an accumulation buffer as a memset on `stream` (gradient arena, statistic sums) */
+int mcb_zero_bytes(void* p, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Convolutions as tcgen05 implicit GEMMs (TMA-fed, TMEM accumulators).
@@ -323,10 +325,6 @@ int mcb_pair_intersections(const int* labels_a, const int* labels_b, int* inter,
  * clen int32 [total], zeroed by the caller */
 int mcb_contour_length(const int* labels, const int* offsets, const int* counts, int* clen, int planes, int h, int w,
                        void* stream);
-
-/* hardware probe used while designing the haloed 3x3 path (debug only, see csrc/probe.cu) */
-int mcb_debug_umma_probe(const void* a, const void* ident, float* out, int rows, int rowb, int shift, int sbo,
-                         int base_off_mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -174,3 +174,11 @@ _SIGS4 = {
 for _n, _a in _SIGS4.items():
     getattr(lib, _n).argtypes = _a
     getattr(lib, _n).restype = ci
+
+lib.mcb_zero_bytes.argtypes = [vp, C.c_size_t, vp]
+lib.mcb_zero_bytes.restype = ci
+
+
+def zero(t):
+    """t.zero_() without a torch kernel: cudaMemsetAsync on the current stream"""
+    fcall("mcb_zero_bytes", t.data_ptr(), t.numel() * t.element_size())

@@ -107,7 +107,7 @@ constexpr int kConvThreads = 320;  // warp 0 TMA producer, warp 1 MMA issuer, wa
 // HALO (3x3, stride 1): the pixel tile is 8 wide x 16 tall in one image and ONE haloed TMA box (BK channels, 10, 18, 1)
 // per channel chunk serves all nine taps: tap (dy, dx) is the same shared-memory tile read through a descriptor whose
 // start is shifted by ((1+dy)*10 + (1+dx)) rows and whose 8-row groups are 10 rows apart (the UMMA swizzle is a function
-// of the absolute shared-memory address, so unaligned starts and a non-atom SBO are legal — csrc/probe.cu,
+// of the absolute shared-memory address, so unaligned starts and a non-atom SBO are legal — tools/probe/probe.cu,
 // tools/probe_umma.py).  A and B then travel in separate mbarrier rings: 1 A load + 9 B loads per channel chunk.
 constexpr int kHaloW = 10, kHaloH = 18;  // (8 + 2) x (16 + 2)
 

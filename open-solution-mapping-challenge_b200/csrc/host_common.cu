@@ -106,4 +106,12 @@ int num_sms() {
 }  // namespace mcb
 
 extern "C" const char* mcb_last_error(void) { return mcb::err_buf(); }
-extern "C" int mcb_version(void) { return 100; }
+extern "C" int mcb_version(void) { return 101; }
+
+// zero-fill of accumulation buffers (gradient arena, BatchNorm statistic sums, loss sums) as a memset node on the caller's
+// stream -- captured into the step's graphs like any launch; no library kernel involved
+extern "C" int mcb_zero_bytes(void* p, size_t bytes, void* stream) {
+  if (!p || bytes == 0) return MCB_OK;
+  MCB_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)));
+  return MCB_OK;
+}

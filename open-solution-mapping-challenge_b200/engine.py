@@ -12,6 +12,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from . import _lib as L
 from . import ops
 
 BF16 = torch.bfloat16
@@ -287,7 +288,7 @@ class Plan:
                 B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma,
                                                               bn0.dbeta, bn0.dgamma, dz0, None, False, self.bn_scale),
                       0, _nb(d_a0, a0, z0, dz0))
-                B.add("misc", lambda: stem_gw.zero_())
+                B.add("misc", lambda: L.zero(stem_gw))
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1), sflops, _nb(dz0, col))
                 B.add("misc", lambda: ops.stem_unpack_wgrad(stem_gw, stem_g))
             self._bwd_builders.append(("stem", build_stem))
@@ -470,7 +471,7 @@ class Plan:
             tab = self._bn_table()
             L.fcall("mcb_bn_eval_params_batched", tab.data_ptr(), len(self._bns), self._bn_maxc, BN_EPS)
         if self.training:
-            self._stats_arena.zero_()
+            L.zero(self._stats_arena)
         for op in self.fwd_ops:
             op()
 
@@ -480,7 +481,7 @@ class Plan:
         `layer_index` (main chain and weight-gradient GEMMs) is ordered before it -- used for per-segment optimizer
         updates that overlap the rest of the backward pass."""
         if first == 0:
-            self.net._g32.zero_()
+            L.zero(self.net._g32)
         # Weight/bias-gradient launches are leaves of the backward graph (they only add into the gradient arena): they
         # go to a side stream, forked after their producer and joined at the end, so the tensor-core-bound wgrad GEMMs
         # overlap the HBM-bound BatchNorm-backward kernels of the layers below instead of queueing behind them.

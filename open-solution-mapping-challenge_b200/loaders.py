@@ -103,8 +103,8 @@ def test_time_augmentation_transform_batch(X, tta_params, img_ids):
     ids = np.asarray(img_ids, np.int32)
     nv = len(codes)
     out = torch.empty((nv, c, h, w), dtype=torch.float32, device=X.device)
-    L.fcall("mcb_tta_transform", X.data_ptr(), out.data_ptr(), torch.from_numpy(ids).to(X.device).data_ptr(),
-            torch.from_numpy(codes).to(X.device).data_ptr(), nv, c, h, w)
+    ids_d, codes_d = torch.from_numpy(ids).to(X.device), torch.from_numpy(codes).to(X.device)   # kept alive past the launch
+    L.fcall("mcb_tta_transform", X.data_ptr(), out.data_ptr(), ids_d.data_ptr(), codes_d.data_ptr(), nv, c, h, w)
     return out
 
 
@@ -126,9 +126,9 @@ def aggregate_batch(pred, tta_params, img_ids, method="gmean", from_logits=False
     var_start = np.concatenate([[0], np.cumsum([int((ids == u).sum()) for u in uniq])]).astype(np.int32)
     dev = pred.device
     out = torch.empty((len(uniq), c, h, w), dtype=torch.float32, device=dev)
-    L.fcall("mcb_tta_aggregate", pred.data_ptr(), int(bool(from_logits)), torch.from_numpy(var_start).to(dev).data_ptr(),
-            torch.from_numpy(order).to(dev).data_ptr(), torch.from_numpy(codes).to(dev).data_ptr(), out.data_ptr(),
-            len(uniq), c, h, w, METHODS[method])
+    start_d, order_d, codes_d = (torch.from_numpy(a).to(dev) for a in (var_start, order, codes))   # kept alive past the launch
+    L.fcall("mcb_tta_aggregate", pred.data_ptr(), int(bool(from_logits)), start_d.data_ptr(), order_d.data_ptr(),
+            codes_d.data_ptr(), out.data_ptr(), len(uniq), c, h, w, METHODS[method])
     return out
 
 

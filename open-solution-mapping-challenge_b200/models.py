@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 from torch import nn, optim
 
+from . import _lib as L
 from . import ops
 from .unet_models import UNetResNet
 
@@ -449,7 +450,7 @@ class FusedTrainStep:
 
     def _loss_partials(self):
         # outside the graphs: it is the first reader of the target, whose H2D copy overlaps the forward segment
-        self.sums.zero_()
+        L.zero(self.sums)
         ops.loss_partials(self.plan.logits, self.target, self.sums, mode=self.loss_mode, **self.loss_cfg)
 
     def _seg_backward(self, seg=None):

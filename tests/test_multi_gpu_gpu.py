@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, sync_bn, out):
+    import faulthandler
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, exit=True)   # a hung collective shows its Python stack and fails fast
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), MCB_SYNC_BN="1" if sync_bn else "0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -34,6 +36,7 @@ def _worker(rank, world, port, sync_bn, out):
     out[rank] = {"losses": losses, "checksum": float(net._p32.double().sum()),
                  "final_w": net.final.weight.detach().float().cpu().numpy().copy(),
                  "bn1_w": net.encoder.bn1.weight.detach().float().cpu().numpy().copy()}
+    faulthandler.cancel_dump_traceback_later()
     dist.destroy_process_group()
 
 

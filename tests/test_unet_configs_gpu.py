@@ -12,10 +12,16 @@ What is asserted, and why the two families:
     33 / 50 un-normalised residual blocks (reference logits reach +-4e3 at ResNet152): an absolute 1e-3 is below fp32's
     own resolution there (4e3 * 2^-24 = 2.4e-4 per operation).  The deviation is asserted RELATIVE to the logits'
     spread and printed.
-  * gradients: decoder-side gradients tight on both; encoder gradients only on the conditioned checkpoint -- at the raw
-    init the reference's own deep gradients are numerically chaotic (|grad| 1e-8..1e-10, cosine ~0 between any two
-    bf16-storage evaluations), on the conditioned checkpoint they are a reproducible quantity.
+  * gradients: decoder-side gradients tight on both checkpoints.  Encoder gradients, conditioned checkpoint: bf16 STORAGE
+    alone (activations, activation gradients, GEMM operands; fp32 accumulation) moves the deep-encoder gradients of
+    these 34 / 101 / 152-layer nets by 14 % .. 99 % relative L2 against the fp32 reference -- measured on the CPU by the
+    bit-faithful emulation oracle/emulated_bf16_deviation.py -> tests/golden/emulated_bf16_deviation.json.  The CUDA path
+    must not be further from the reference than that emulation (x1.15 + 0.01): its deviation IS the storage format's,
+    tensor by tensor (first hardware run: 0.2679 vs 0.2702, 0.7475 vs 0.7615, 0.9676 vs 0.9870, ... at ResNet152).
+    At the raw init the deep gradients are numerically chaotic (|grad| 1e-8..1e-10, cosine ~0 between ANY two
+    bf16-storage evaluations) and only their finiteness is checked.
 """
+import json
 import os
 
 import numpy as np
@@ -105,11 +111,9 @@ def test_conditioned_checkpoint_against_reference(mcb, cuda, case):
     assert abs(r["loss"] - r["loss_ref"]) < 1e-4 * abs(r["loss_ref"])
     for k in DECODER_TAIL:
         assert r["grads"][k][0] < 2e-2, (k, r["grads"][k])
+    emu = json.load(open(os.path.join(GOLD, "emulated_bf16_deviation.json")))[r["tag"]]
+    assert abs(tr_err - emu["logits_max_abs"]) < 1e-4      # the logits' deviation is the storage format's as well
     for k, (rel, cos) in r["grads"].items():
-        if k.startswith("encoder.") or k.startswith(("center", "dec3")):
-            assert cos > ENCODER_COS[case] and rel < ENCODER_REL[case], (k, rel, cos)
-
-
-# bars set from the first hardware run (printed above); bf16 storage through 16 / 33 / 50 residual blocks
-ENCODER_COS = (0.99, 0.98, 0.97)
-ENCODER_REL = (0.15, 0.2, 0.25)
+        e = emu["grads"][k]
+        assert rel <= 1.15 * e["rel"] + 0.01, (k, "rel", rel, "emulated bf16 storage", e["rel"])
+        assert cos >= e["cos"] - 0.05, (k, "cos", cos, "emulated bf16 storage", e["cos"])

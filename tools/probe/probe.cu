@@ -3,9 +3,9 @@
 // not a multiple of the atom?  This decides whether one haloed activation tile can serve all nine taps of a 3x3 conv.
 // D[m][n] = A[m][n] with B = identity, A rows taken from a TMA-written (swizzled) R x (ROWB bytes) tile:
 //   row(m) = shift + (m / 8) * (sbo / ROWB) + m % 8.
-#include "host_common.h"
-#include "tc.cuh"
-#include "../../include/mcb200.h"
+#include "../../open-solution-mapping-challenge_b200/csrc/host_common.h"
+#include "../../open-solution-mapping-challenge_b200/csrc/tc.cuh"
+
 
 namespace mcb {
 

@@ -1,4 +1,7 @@
-"""Runs csrc/probe.cu over row shifts / stride offsets / base-offset modes and reports which descriptor forms read the
+"""(design-time tool, not part of the product build: compile tools/probe/probe.cu into its own library first --
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC tools/probe/probe.cu
+open-solution-mapping-challenge_b200/csrc/host_common.cu -o gpurun_out/libprobe.so -- and point L.lib at it.)
+Runs tools/probe/probe.cu over row shifts / stride offsets / base-offset modes and reports which descriptor forms read the
 expected rows of a swizzled TMA tile."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
