@@ -326,6 +326,29 @@ int mcb_pair_intersections(const int* labels_a, const int* labels_b, int* inter,
 int mcb_contour_length(const int* labels, const int* offsets, const int* counts, int* clen, int planes, int h, int w,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Input side: the step right before the network.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* padding_seq (src/augmentation.py:40-86 -> cv2.copyMakeBorder, pad_mode 0 = BORDER_REPLICATE, 1 = BORDER_REFLECT_101)
+ * + transforms.ToTensor + transforms.Normalize (src/loaders.py:311-317): img uint8 [n][h][w][3] -> out fp32
+ * [n][3][h + 2 pad_h][w + 2 pad_w]; mean3 / std3 are HOST pointers to three floats; bit-exact fp32 */
+int mcb_image_pad_normalize(const uint8_t* img, float* out, int n, int h, int w, int pad_h, int pad_w, int pad_mode,
+                            const float* mean3, const float* std3, void* stream);
+/* update_distances + clean_distances (src/preparation.py:151-168): masks uint8 [k][h][w] (one plane per building of ONE
+ * image, non-empty); dist_sum fp16 [h][w] = d_nearest + d_second (one building counts twice, none gives 0),
+ * second_nearest fp64 [h][w]; distances are scipy.ndimage.distance_transform_edt(1 - mask), exact;
+ * workspace int32 [k][h][w] */
+int mcb_edt_two_nearest(const uint8_t* masks, int k, int h, int w, int* workspace, void* dist_sum_f16,
+                        double* second_nearest, void* stream);
+/* get_size_matrix (src/preparation.py:189-195): labels int32 [h][w] (mcb_ccl_label), area int32 [labels] -> int64 [h][w] */
+int mcb_size_matrix(const int* labels, const int* area, long long* out, int h, int w, void* stream);
+/* the target tensor of MetadataImageSegmentationDatasetDistances (src/loaders.py:141-171), deterministic part:
+ * mask uint8 [n][h][w], dist fp16 [n][h][w], sizes int64 [n][h][w] -> fp32 [n][3][h + 2 pad_h][w + 2 pad_w] =
+ * {mask, uint8(uint16(dist)), uint8(uint16(sqrt(uint16(sizes))))}, padded like the image */
+int mcb_target_channels(const uint8_t* mask, const void* dist_f16, const long long* sizes, float* out, int n, int h, int w,
+                        int pad_h, int pad_w, int pad_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

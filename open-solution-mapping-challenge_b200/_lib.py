@@ -182,3 +182,13 @@ lib.mcb_zero_bytes.restype = ci
 def zero(t):
     """t.zero_() without a torch kernel: cudaMemsetAsync on the current stream"""
     fcall("mcb_zero_bytes", t.data_ptr(), t.numel() * t.element_size())
+
+_SIGS5 = {
+    "mcb_image_pad_normalize": [vp, vp, ci, ci, ci, ci, ci, ci, fp, fp, vp],
+    "mcb_edt_two_nearest": [vp, ci, ci, ci, vp, vp, vp, vp],
+    "mcb_size_matrix": [vp, vp, vp, ci, ci, vp],
+    "mcb_target_channels": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+}
+for _n, _a in _SIGS5.items():
+    getattr(lib, _n).argtypes = _a
+    getattr(lib, _n).restype = ci

@@ -117,7 +117,9 @@ static int pick_bn(int n_total, long m_tiles, int phases) {
   // keep the machine filled when the pixel dimension is small
   const long sms = num_sms();
   // (fat tiles beat many thin ones: go below 128 only when even 128-wide tiles leave most SMs idle)
-  if (bn > 128 && m_tiles * phases * (n_total / bn) < sms) bn = 128;
+  // (measured, gpurun r2 sweep: at 100 pixel tiles -- layer3's 20x20 maps -- ONE round of 256-wide tiles beats two
+  // rounds of 128-wide ones by 7-15 %; at 25 pixel tiles the 128-wide split wins 25 %: switch below ~0.6 of a wave)
+  if (bn > 128 && m_tiles * phases * (n_total / bn) * 10 < sms * env_int("MCB_BN256_MIN_WAVE_X10", 6)) bn = 128;
   if (bn > 64 && n_total % 64 == 0 && m_tiles * phases * (n_total / bn) < sms / 3) bn = 64;
   int forced = env_int("MCB_FORCE_BN", 0);
   if (forced && n_total % forced == 0) bn = forced;

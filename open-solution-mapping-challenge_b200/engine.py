@@ -467,7 +467,6 @@ class Plan:
 
     def _run_fwd(self):
         if not self.training:
-            from . import _lib as L
             tab = self._bn_table()
             L.fcall("mcb_bn_eval_params_batched", tab.data_ptr(), len(self._bns), self._bn_maxc, BN_EPS)
         if self.training:
