@@ -464,6 +464,19 @@ def infer_reference_line(args):
 _REAL_STDOUT = None
 
 
+def finish_distributed():
+    """orderly multi-GPU exit: every rank is done computing; captured graphs hold NCCL work, so skip the communicator
+    teardown (it can wait forever on them) and leave with status 0"""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
 def emit(line):
     """the ONE JSON line goes to the real stdout; everything else this process (or NCCL's banner, printed from C) writes
     to fd 1 has been rerouted to stderr by main()"""
@@ -538,7 +551,7 @@ def main():
         if rank == 0:
             emit(line)
         if world > 1:
-            dist.destroy_process_group()
+            finish_distributed()
         return
     import mcb200
     from mcb200.models import PyTorchUNetWeighted
@@ -548,7 +561,7 @@ def main():
         if rank == 0:
             emit(line)
         if world > 1:
-            dist.destroy_process_group()
+            finish_distributed()
         return
 
     t_start = time.time()
@@ -646,7 +659,7 @@ def main():
     fused = model._fused
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            finish_distributed()
         return
     peak_tf, peak_hbm, peak_src = peaks()
     fpt = FLOP_PER_TILE.get((args.encoder, args.size))
@@ -658,7 +671,10 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": tiles, "parallelism": "dp%d" % world,
-                   "bn": "per-replica batch statistics (reference DataParallel semantics)" if world > 1 else "batch statistics",
+                   "bn": ("synchronised over the global batch (MCB_SYNC_BN=%s)" % os.environ.get("MCB_SYNC_BN") if fused.plan.sync_bn
+                          else "per-replica batch statistics (reference DataParallel semantics)") if world > 1 else "batch statistics",
+                   "grad_allreduce": ("in-graph, per arena segment, overlapped with the backward pass" if fused.inline_allreduce
+                                      else "one call after the backward graph") if world > 1 else None,
                    "replicas_in_sync": in_sync,
                    "l2": "per-step working set (activations + gradients, GBs) far exceeds the 126 MB L2; no flush needed",
                    "loss_last_step": loss_dev},
@@ -707,7 +723,7 @@ def main():
         note("cpu baseline done")
     emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        finish_distributed()
 
 
 if __name__ == "__main__":

@@ -349,6 +349,19 @@ int mcb_size_matrix(const int* labels, const int* area, long long* out, int h, i
 int mcb_target_channels(const uint8_t* mask, const void* dist_f16, const long long* sizes, float* out, int n, int h, int w,
                         int pad_h, int pad_w, int pad_mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Synchronised BatchNorm over NVLink peer memory (SURVEY.md 8e collective (2)): one-shot all-reduce of a small fp32
+ * vector.  peer_bufs / peer_flags: DEVICE arrays of `world` pointers, entry r = rank r's symmetric buffer as mapped in
+ * this process (caller's plumbing, e.g. torch symmetric memory); flags: uint32 [exchanges][world] per rank, zeroed once.
+ * out[c] = sum over ranks (in rank order) of peer_bufs[r][offset + c]; optionally out2_first[c] / out2_second[c - split]
+ * = scale2 * out[c].  `exchange` numbers the exchange inside a step, *step is the device-resident step stamp
+ * (mcb_sync_step_bump at the start of every step).  Asynchronous on `stream`, capturable.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int mcb_sync_step_bump(unsigned* step, void* stream);
+int mcb_sync_exchange(const float* const* peer_bufs, unsigned* const* peer_flags, int rank, int world, long offset,
+                      int count, int exchange, const unsigned* step, float* out, float* out2_first, float* out2_second,
+                      int split, float scale2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

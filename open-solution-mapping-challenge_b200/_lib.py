@@ -192,3 +192,8 @@ _SIGS5 = {
 for _n, _a in _SIGS5.items():
     getattr(lib, _n).argtypes = _a
     getattr(lib, _n).restype = ci
+
+lib.mcb_sync_step_bump.argtypes = [vp, vp]
+lib.mcb_sync_step_bump.restype = ci
+lib.mcb_sync_exchange.argtypes = [vp, vp, ci, ci, cl, ci, ci, vp, vp, vp, vp, ci, cf, vp]
+lib.mcb_sync_exchange.restype = ci

@@ -52,7 +52,8 @@ class _OpList(list):
 
 class _BN:
     """per-BatchNorm device state"""
-    __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta", "tr")
+    __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta", "tr",
+                 "idx", "off", "app_dgamma", "app_dbeta", "g32_dgamma", "g32_dbeta")
 
 
 class Plan:
@@ -68,6 +69,7 @@ class Plan:
         self._bwd_builders = []    # one per forward unit; run in REVERSE so store/accumulate modes follow run order
         self.units = []            # (kind, state_dict prefix, inputs, output) per forward unit, for per-unit parity tests
         total_c = sum(m.num_features for m in net.modules() if isinstance(m, nn.BatchNorm2d))
+        n_bn = sum(1 for m in net.modules() if isinstance(m, nn.BatchNorm2d))
         self._stats_arena = torch.zeros(2 * total_c, dtype=F32, device=self.dev)
         self._stats_used = 0
         self.graph_fwd = self.graph_bwd = None
@@ -78,8 +80,33 @@ class Plan:
         # semantics (per-replica statistics, src/models.py:65).  The collectives are issued from the plan, so they are
         # captured into the step's CUDA graphs with everything else.
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        self.sync_bn = training and self.world > 1 and os.environ.get("MCB_SYNC_BN", "0") == "1"
+        mode = os.environ.get("MCB_SYNC_BN", "0")
+        self.sync_bn = training and self.world > 1 and mode in ("1", "2")
+        # MCB_SYNC_BN=2: the per-BatchNorm exchange is a one-shot all-reduce over NVLink peer memory (csrc/sync.cu) instead
+        # of a NCCL call: partial sums live in symmetric memory, global sums land in local buffers
+        self.sync_nvlink = self.sync_bn and mode == "2"
         self.bn_scale = self.world if self.sync_bn else 1
+        if self.sync_nvlink:
+            import torch.distributed._symmetric_memory as symm
+            grp = dist.group.WORLD
+            self.rank = dist.get_rank()
+
+            def sym(n, dtype):
+                t = symm.empty(n, dtype=dtype, device=self.dev)
+                t.zero_()
+                h = symm.rendezvous(t, grp)
+                ptrs = torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=self.dev)
+                self._keep.append(h)
+                return t, ptrs
+            self._stats_arena, self._peer_stats = sym(2 * total_c, F32)          # conv epilogues accumulate here
+            self._dstats_sym, self._peer_dstats = sym(2 * total_c, F32)          # [dbeta | dgamma] partial sums
+            self._flags_sym, self._peer_flags = sym(2 * n_bn * self.world, torch.int32)
+            self._gstats = torch.zeros(2 * total_c, dtype=F32, device=self.dev)    # global [sum, sum^2]
+            self._gdstats = torch.zeros(2 * total_c, dtype=F32, device=self.dev)   # global [dbeta | dgamma]
+            self._sync_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._n_bn = n_bn
+            torch.cuda.synchronize()
+            dist.barrier()
         self.bias_sum = {}         # id(conv+bias+ReLU output) -> its bias-gradient vector (fused into the consumer's dgrad)
         self.bias_fused = set()
         self.x_in = torch.zeros((n, 3, h, w), dtype=F32, device=self.dev)
@@ -122,12 +149,23 @@ class Plan:
         c = b.c
         buf = torch.zeros(4 * c, dtype=F32, device=self.dev)
         self._keep.append(buf)
+        b.idx, b.off = len(self._bns), self._stats_used
         b.stats = self._stats_arena[self._stats_used:self._stats_used + 2 * c]
         self._stats_used += 2 * c
         b.scale, b.shift, b.mean, b.invstd = buf[:c], buf[c:2 * c], buf[2 * c:3 * c], buf[3 * c:4 * c]
         b.gamma, b.beta = net._vec(mod.weight, net._p32), net._vec(mod.bias, net._p32)
-        b.dgamma, b.dbeta = net._vec(mod.weight, net._g32), net._vec(mod.bias, net._g32)
-        b.tr = ops.make_bn_train(b.stats, b.gamma, b.beta, mod.running_mean, mod.running_var, b.mean, b.invstd) \
+        b.g32_dgamma, b.g32_dbeta = net._vec(mod.weight, net._g32), net._vec(mod.bias, net._g32)
+        if self.sync_nvlink:
+            # the reduction kernels accumulate this rank's partial sums in symmetric memory; the exchange writes the
+            # global sums to local buffers (what the normalisation passes read) and global / world to the gradient slots
+            b.dbeta, b.dgamma = self._dstats_sym[b.off:b.off + c], self._dstats_sym[b.off + c:b.off + 2 * c]
+            b.app_dbeta, b.app_dgamma = self._gdstats[b.off:b.off + c], self._gdstats[b.off + c:b.off + 2 * c]
+            tr_stats = self._gstats[b.off:b.off + 2 * c]
+        else:
+            b.dgamma, b.dbeta = b.g32_dgamma, b.g32_dbeta
+            b.app_dgamma, b.app_dbeta = b.dgamma, b.dbeta
+            tr_stats = b.stats
+        b.tr = ops.make_bn_train(tr_stats, b.gamma, b.beta, mod.running_mean, mod.running_var, b.mean, b.invstd) \
             if self.training else None
         self._bns.append(b)
         return b
@@ -177,14 +215,23 @@ class Plan:
 
     def sync_stats(self, F, bn):
         """SyncBN forward: sum the per-rank [sum, sum^2] before the BN apply pass reads them"""
-        if self.sync_bn:
+        if self.sync_nvlink:
+            F.add("bn_exchange", lambda: L.fcall(
+                "mcb_sync_exchange", self._peer_stats.data_ptr(), self._peer_flags.data_ptr(), self.rank, self.world,
+                bn.off, 2 * bn.c, bn.idx, self._sync_step.data_ptr(), self._gstats[bn.off:].data_ptr(), None, None, 0, 0.0))
+        elif self.sync_bn:
             F.add("bn_allreduce", lambda: dist.all_reduce(bn.stats))
 
     def sync_bn_grads(self, B, bn):
         """SyncBN backward: dz needs the GLOBAL dbeta / dgamma.  They are the parameter-gradient slots themselves, so
         after this they hold the global sums on every rank (FusedTrainStep divides them by the world size before the
         arena-wide gradient all-reduce adds the ranks up again)."""
-        if self.sync_bn:
+        if self.sync_nvlink:
+            B.add("bn_exchange", lambda: L.fcall(
+                "mcb_sync_exchange", self._peer_dstats.data_ptr(), self._peer_flags.data_ptr(), self.rank, self.world,
+                bn.off, 2 * bn.c, self._n_bn + bn.idx, self._sync_step.data_ptr(), self._gdstats[bn.off:].data_ptr(),
+                bn.g32_dbeta.data_ptr(), bn.g32_dgamma.data_ptr(), bn.c, 1.0 / self.world))
+        elif self.sync_bn:
             g32 = self.net._g32
             lo = (bn.dgamma.data_ptr() - g32.data_ptr()) // 4
             hi = (bn.dbeta.data_ptr() - g32.data_ptr()) // 4
@@ -210,8 +257,8 @@ class Plan:
             B.add("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(dy, ymask, z, bn.mean, bn.invstd, bn.dbeta, bn.dgamma),
                   0, _nb(dy, ymask, z))
         self.sync_bn_grads(B, bn)
-        B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.dbeta, bn.dgamma,
-                                                      dz, g_out, g_out_acc, self.bn_scale), 0,
+        B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.app_dbeta,
+                                                      bn.app_dgamma, dz, g_out, g_out_acc, self.bn_scale), 0,
               _nb(dy, ymask, z, dz, g_out))
         desc = "%d->%d k%d s%d @%dx%dx%d" % (x.shape[3], dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2])
         B.add("conv_wgrad", lambda: ops.conv_wgrad(dz, x, gw, k, s), 2.0 * dz.numel() * x.shape[3] * k * k,
@@ -286,7 +333,8 @@ class Plan:
                                                                 bn0.dgamma), 0, _nb(d_a0, a0, z0))
                 self.sync_bn_grads(B, bn0)
                 B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma,
-                                                              bn0.dbeta, bn0.dgamma, dz0, None, False, self.bn_scale),
+                                                              bn0.app_dbeta, bn0.app_dgamma, dz0, None, False,
+                                                              self.bn_scale),
                       0, _nb(d_a0, a0, z0, dz0))
                 B.add("misc", lambda: L.zero(stem_gw))
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1), sflops, _nb(dz0, col))
@@ -470,6 +518,8 @@ class Plan:
             tab = self._bn_table()
             L.fcall("mcb_bn_eval_params_batched", tab.data_ptr(), len(self._bns), self._bn_maxc, BN_EPS)
         if self.training:
+            if self.sync_nvlink:
+                L.fcall("mcb_sync_step_bump", self._sync_step.data_ptr())
             L.zero(self._stats_arena)
         for op in self.fwd_ops:
             op()
@@ -481,6 +531,8 @@ class Plan:
         updates that overlap the rest of the backward pass."""
         if first == 0:
             L.zero(self.net._g32)
+            if self.sync_nvlink:
+                L.zero(self._dstats_sym)
         # Weight/bias-gradient launches are leaves of the backward graph (they only add into the gradient arena): they
         # go to a side stream, forked after their producer and joined at the end, so the tensor-core-bound wgrad GEMMs
         # overlap the HBM-bound BatchNorm-backward kernels of the layers below instead of queueing behind them.
@@ -542,18 +594,21 @@ class Plan:
             main.wait_event(ev)
 
     def bwd_segments(self):
-        """split points for overlapping the gradient all-reduce with the backward pass: [decoder | layer4 | rest].
-        -> [(first_layer, last_layer, arena_lo, arena_hi)], arena ranges complete when the segment has run"""
+        """split points for overlapping the gradient all-reduce / the Adam update with the backward pass:
+        [decoder | layer4 | layer3 | rest].  -> [(first_layer, last_layer, arena_lo, arena_hi)], the arena range is
+        complete once the segment has run (layer3's 23 blocks reduce while layer2 / layer1 / stem still run)"""
         net = self.net
         tags = self.bwd_tags
         n = len(tags)
         i_dec = max(i for i, t in enumerate(tags) if t == "decoder") + 1
         i_l4 = max(i for i, t in enumerate(tags) if t == "layer4") + 1
+        i_l3 = max(i for i, t in enumerate(tags) if t == "layer3") + 1
         off = {name: net._slots[id(p)].off for name, p, _ in net._arena_params()}
         total = net._p32.numel()
         o_dec = off["center.block.0.conv.weight"]
         o_l4 = off["encoder.layer4.0.conv1.weight"]
-        return [(0, i_dec, o_dec, total), (i_dec, i_l4, o_l4, o_dec), (i_l4, n, 0, o_l4)]
+        o_l3 = off["encoder.layer3.0.conv1.weight"]
+        return [(0, i_dec, o_dec, total), (i_dec, i_l4, o_l4, o_dec), (i_l4, i_l3, o_l3, o_l4), (i_l3, n, 0, o_l3)]
 
     def forward(self, x, use_graph=True):
         self.x_in.copy_(x)

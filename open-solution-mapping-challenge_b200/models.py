@@ -128,6 +128,20 @@ def callbacks_unet(callbacks_config):
     return reference_callbacks_unet(callbacks_config)
 
 
+def release_captured_graphs(transformer):
+    """drop every captured CUDA graph / launch plan of a transformer.  Call it before
+    torch.distributed.destroy_process_group(): graphs that captured NCCL collectives keep the communicator busy and the
+    teardown waits on them forever (seen on 2 GPUs, gpurun r2)."""
+    import gc
+    transformer._fused = None
+    transformer._fused_cache = {}
+    net = transformer._net()
+    net._plans = {}
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
 def weight_regularization_unet(model, regularize, weight_decay_conv2d):
     """src/models.py:287-292"""
     if regularize:
@@ -430,14 +444,20 @@ class FusedTrainStep:
         self.segments = None
         # opt-in: on 2 GPUs the three smaller all-reduces + graph segmentation cost more than they hide (22.8 vs 22.3
         # ms/step, gpurun r1); kept for larger worlds / slower fabrics
-        if self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "1" and not self.plan.sync_bn:
+        if self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "2") == "1" and not self.plan.sync_bn:
             self.segments = self.plan.bwd_segments()
             self._comm_stream = torch.cuda.Stream(device=dev)
         # single GPU: the Adam update of a finished arena segment (decoder | layer4 | rest) rides on the backward's side
         # stream, inside the graph, overlapping the data-gradient GEMMs of the layers below (HBM-bound next to
         # tensor-bound).  Its step-dependent scalars live in a 3-float device tensor refreshed before every replay.
-        self.inline_allreduce = (self.world > 1 and os.environ.get("MCB_OVERLAP_ALLREDUCE", "0") == "2"
-                                 and not self.plan.sync_bn)
+        # multi-GPU default: the all-reduce of a finished arena segment (decoder | layer4 | layer3 | rest) is issued from
+        # INSIDE the backward graph, on the side stream behind that segment's weight-gradient GEMMs, and overlaps the
+        # data-gradient chain of the layers below (gpurun r2, N=2: 16.97 vs 17.21 ms/step with one exposed all-reduce).
+        # MCB_OVERLAP_ALLREDUCE=0 restores the single all-reduce after the backward graph; NCCL-per-BatchNorm SyncBN
+        # (MCB_SYNC_BN=1) needs it because its BatchNorm slots are rescaled after the backward pass.
+        ov = os.environ.get("MCB_OVERLAP_ALLREDUCE", "2")
+        self.inline_allreduce = (self.world > 1 and ov == "2" and self.segments is None
+                                 and not (self.plan.sync_bn and not self.plan.sync_nvlink))
         self.adam_in_graph = self.world == 1 and os.environ.get("MCB_ADAM_SIDE", "1") == "1"
         self._hyper = torch.zeros(3, dtype=torch.float32, device=dev)
         # pinned staging ring: a slot is rewritten only after the copy that last read it has executed
@@ -568,7 +588,7 @@ class FusedTrainStep:
             else:
                 self.graphs[1].replay()
             if self.world > 1 and not self.inline_allreduce:
-                if self.plan.sync_bn:
+                if self.plan.sync_bn and not self.plan.sync_nvlink:
                     # the BatchNorm slots already hold GLOBAL sums (engine.Plan.sync_bn_grads): pre-divide so that the
                     # arena-wide SUM below leaves them unchanged
                     torch._foreach_mul_(self.plan.bn_grad_slices(), 1.0 / self.world)

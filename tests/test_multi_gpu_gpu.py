@@ -19,7 +19,7 @@ def _worker(rank, world, port, sync_bn, out):
     import faulthandler
     import torch.distributed as dist
     faulthandler.dump_traceback_later(150, exit=True)   # a hung collective shows its Python stack and fails fast
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), MCB_SYNC_BN="1" if sync_bn else "0")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), MCB_SYNC_BN=str(int(sync_bn)))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import bench
@@ -37,13 +37,17 @@ def _worker(rank, world, port, sync_bn, out):
                  "final_w": net.final.weight.detach().float().cpu().numpy().copy(),
                  "bn1_w": net.encoder.bn1.weight.detach().float().cpu().numpy().copy()}
     faulthandler.cancel_dump_traceback_later()
+    from mcb200.models import release_captured_graphs
+    release_captured_graphs(model)        # graphs that captured NCCL work must go before the communicator does
+    faulthandler.dump_traceback_later(60, exit=True)
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
 
 
 def _run_two_ranks(sync_bn):
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29700 + (os.getpid() % 1000) + (50 if sync_bn else 0)
+    port = 29700 + (os.getpid() % 1000) + 50 * int(sync_bn)
     mp.spawn(_worker, args=(2, port, sync_bn, out), nprocs=2, join=True)
     return out[0], out[1]
 
@@ -67,7 +71,9 @@ def test_replicas_stay_identical_with_per_replica_batchnorm(mcb, two_gpus):
 @pytest.mark.skipif(os.environ.get("MCB_TEST_SYNC_BN") != "1",
                     reason="synchronised BatchNorm is an opt-in that has not run on hardware yet (DESIGN.md section 5): "
                            "set MCB_TEST_SYNC_BN=1 on a >= 2-GPU box")
-def test_sync_bn_reproduces_the_single_process_global_batch(mcb, two_gpus):
+@pytest.mark.parametrize("mode", [2, 1])
+def test_sync_bn_reproduces_the_single_process_global_batch(mcb, two_gpus, mode):
+    """mode 1: one NCCL all-reduce per BatchNorm; mode 2: the one-shot exchange over NVLink peer memory (csrc/sync.cu)"""
     import bench
     from mcb200.models import PyTorchUNetWeighted
     torch.manual_seed(77)
@@ -78,7 +84,7 @@ def test_sync_bn_reproduces_the_single_process_global_batch(mcb, two_gpus):
     ref_losses = [float(model._fit_loop([X, T])["sum"]) for _ in range(3)]
     ref_final = model._net().final.weight.detach().float().cpu().numpy()
     ref_bn1 = model._net().encoder.bn1.weight.detach().float().cpu().numpy()
-    r0, r1 = _run_two_ranks(sync_bn=True)
+    r0, r1 = _run_two_ranks(sync_bn=mode)
     assert r0["checksum"] == r1["checksum"]
     for a, b in zip(r0["losses"], ref_losses):
         assert abs(a - b) < 2e-3 * abs(b), (r0["losses"], ref_losses)
