@@ -653,6 +653,16 @@ def main():
         if not in_sync:
             raise RuntimeError("replicas diverged (parameter checksums %r): gradient all-reduce missing?" % (vals,))
 
+    # phase split of the captured step (CUDA events between the graph replays), averaged over 5 extra steps
+    phases = {}
+    fz = model._fused
+    for _ in range(5):
+        fz.phase_marks = []
+        step_dev()
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(fz.phase_marks[:-1], fz.phase_marks[1:]):
+            phases[n1] = phases.get(n1, 0.0) + e0.elapsed_time(e1) / 5
+    fz.phase_marks = None
     tiles = args.batch * world
     value = tiles / (ms_dev * 1e-3)
     e2e = tiles / (ms_e2e * 1e-3)
@@ -682,6 +692,7 @@ def main():
                 "h2d_bytes_per_step": int(Xh.numel() * 4 + Th.numel() * 4), "d2h_bytes_per_step": 4,
                 "api": "mcb200.models.PyTorchUNetWeighted._fit_loop([X_host_pinned, target_host_pinned]) + async D2H of the loss into pinned memory, consumed one step later"},
         "gpu_launches": fused.count_launches() * args.steps,
+        "phases_ms": {k: round(v, 3) for k, v in phases.items()},
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,

@@ -306,13 +306,14 @@ int mcb_tta_aggregate(const float* pred, int from_logits, const int* var_start, 
 int mcb_instance_geometry(const int* labels, const void* prob, int prob_is_f64, const int* offsets, const int* counts,
                           int* geo, double* psum, int* pmax, int planes, int h, int w, void* stream);
 /* COCO run-length encoding of every instance mask (pycocotools rleEncode on the Fortran-ordered mask,
- * src/utils.py:118-120): pass write=0 fills nchanges[slot] = number of value changes of the column-major scan; the
- * caller prefix-sums it into out_start; pass write=1 stores the change positions at changes[out_start[slot]...] and
- * spans[slot] = 1 when a run of ones covers several columns (rleToBbox then reports the full height).
- * inst_plane int32 [total] = plane of each slot */
-int mcb_rle_walk(const int* labels, const int* offsets, const int* counts, const int* geo, const int* inst_plane,
-                 const int* out_start, int* nchanges, int* changes, int* spans, int total, int h, int w, int write,
-                 void* stream);
+ * src/utils.py:118-120).  One task per (instance, bounding-box column), listed in (instance, column) order by the caller
+ * (task_slot, task_x: int32 [ntasks]).  Pass write=0 fills task_n[t] = number of value changes of the column-major scan
+ * inside that column; the caller prefix-sums it into task_start; pass write=1 stores the change positions (x*h + y) at
+ * changes[task_start[t]...] and sets spans[slot] when a run of ones covers several columns (rleToBbox then reports the
+ * full height).  inst_plane int32 [instances] = plane of each slot; geo from mcb_instance_geometry */
+int mcb_rle_walk(const int* labels, const int* offsets, const int* geo, const int* inst_plane, const int* task_slot,
+                 const int* task_x, const int* task_start, int* task_n, int* changes, int* spans, int ntasks, int h, int w,
+                 int write, void* stream);
 /* run lengths from change positions: instance `slot` owns counts [out_start[slot] + slot, +nchanges[slot] + 1);
  * slot_of_count int32 [total_counts]; cnts uint32 [total_counts] */
 int mcb_rle_counts(const int* changes, const int* nchanges, const int* out_start, const int* slot_of_count,
@@ -351,16 +352,19 @@ int mcb_target_channels(const uint8_t* mask, const void* dist_f16, const long lo
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Synchronised BatchNorm over NVLink peer memory (SURVEY.md 8e collective (2)): one-shot all-reduce of a small fp32
- * vector.  peer_bufs / peer_flags: DEVICE arrays of `world` pointers, entry r = rank r's symmetric buffer as mapped in
- * this process (caller's plumbing, e.g. torch symmetric memory); flags: uint32 [exchanges][world] per rank, zeroed once.
- * out[c] = sum over ranks (in rank order) of peer_bufs[r][offset + c]; optionally out2_first[c] / out2_second[c - split]
- * = scale2 * out[c].  `exchange` numbers the exchange inside a step, *step is the device-resident step stamp
- * (mcb_sync_step_bump at the start of every step).  Asynchronous on `stream`, capturable.
+ * vector.  `partial` = this rank's partial sums (local memory, [stride] floats, this exchange at [offset, offset+count)).
+ * peer_recv / peer_flags: DEVICE arrays of `world` pointers, entry r = rank r's symmetric buffer as mapped in this
+ * process (caller's plumbing, e.g. torch symmetric memory): recv fp32 [world][stride] per rank, flags uint32
+ * [exchanges][world] per rank, zeroed once.  The kernel pushes partial[offset..] into slot [rank] of every peer's recv,
+ * stamps the flags, waits for the peers' stamps and writes out[c] = sum over ranks (in rank order); optionally
+ * out2_first[c] / out2_second[c - split] = scale2 * out[c].  `exchange` numbers the exchange inside a step, *step is the
+ * device-resident step stamp (mcb_sync_step_bump at the start of every step).  count, offset, stride multiples of 4.
+ * Asynchronous on `stream`, capturable.
  * ---------------------------------------------------------------------------------------------------------------- */
 int mcb_sync_step_bump(unsigned* step, void* stream);
-int mcb_sync_exchange(const float* const* peer_bufs, unsigned* const* peer_flags, int rank, int world, long offset,
-                      int count, int exchange, const unsigned* step, float* out, float* out2_first, float* out2_second,
-                      int split, float scale2, void* stream);
+int mcb_sync_exchange(const float* partial, float* const* peer_recv, unsigned* const* peer_flags, int rank, int world,
+                      long stride, long offset, int count, int exchange, const unsigned* step, float* out,
+                      float* out2_first, float* out2_second, int split, float scale2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -166,7 +166,7 @@ _SIGS4 = {
     "mcb_tta_transform": [vp, vp, vp, vp, ci, ci, ci, ci, vp],
     "mcb_tta_aggregate": [vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
     "mcb_instance_geometry": [vp, vp, ci, vp, vp, vp, vp, vp, ci, ci, ci, vp],
-    "mcb_rle_walk": [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp],
+    "mcb_rle_walk": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp],
     "mcb_rle_counts": [vp, vp, vp, vp, vp, cl, ci, vp],
     "mcb_pair_intersections": [vp, vp, vp, ci, ci, ci, ci, vp],
     "mcb_contour_length": [vp, vp, vp, vp, ci, ci, ci, vp],
@@ -195,5 +195,5 @@ for _n, _a in _SIGS5.items():
 
 lib.mcb_sync_step_bump.argtypes = [vp, vp]
 lib.mcb_sync_step_bump.restype = ci
-lib.mcb_sync_exchange.argtypes = [vp, vp, ci, ci, cl, ci, ci, vp, vp, vp, vp, ci, cf, vp]
+lib.mcb_sync_exchange.argtypes = [vp, vp, vp, ci, ci, cl, cl, ci, ci, vp, vp, vp, vp, ci, cf, vp]
 lib.mcb_sync_exchange.restype = ci

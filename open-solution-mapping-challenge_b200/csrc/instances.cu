@@ -186,61 +186,58 @@ __global__ void __launch_bounds__(256) instance_geometry_kernel(const int* __res
 // lengths of alternating runs, starting with a (possibly empty) run of zeros.  Equivalently: the sorted list of
 // positions p (column-major, p = x*H + y) where the mask value differs from the value at p-1 (value 0 before the
 // start); counts = differences of consecutive change positions, closed by H*W - last.
-// One warp per instance walks the columns of its bounding box [cmin, cmax] x [rmin, rmax] 32 rows at a time; a run that
-// ends at the last row of a column and resumes at the first row of the next (only possible when the box spans the full
-// height) is one run, exactly as in the linear scan.  Pass 1 (write == 0) counts the changes, pass 2 writes them.
-// spans[slot] is set when some run of ones covers more than one column (rleToBbox then reports the full height).
+// The columns of an instance's bounding box [cmin, cmax] x [rmin, rmax] are INDEPENDENT tasks (one warp each, 32 rows
+// per step): the scan's state on entering column x is 0 unless the box spans the full image height, in which case it
+// is the instance's value at (H-1, x-1) -- one extra load, no serial dependency between columns (the background layer
+// of every image is one instance as large as the image; walking its 300 columns serially took 1 ms).  A run that is
+// still on at the last box row of a column ends at x*H + rmax + 1 unless the box spans the full height (then the next
+// column's first pixel decides).  task_slot / task_x list the (instance, column) tasks in (instance, column) order, so
+// change positions come out sorted.  Pass 1 (write == 0) counts the changes of each task, pass 2 writes them at
+// task_start[t].  spans[slot] is set when a run of ones covers more than one column (rleToBbox then reports the full
+// height).
 __global__ void __launch_bounds__(128) rle_walk_kernel(const int* __restrict__ labels, const int* __restrict__ offsets,
-                                                       const int* __restrict__ counts, const int* __restrict__ geo,
-                                                       const int* __restrict__ inst_plane, const int* __restrict__ out_start,
-                                                       int* __restrict__ nchanges, int* __restrict__ changes,
-                                                       int* __restrict__ spans, int total, int H, int W, int write) {
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                       const int* __restrict__ geo, const int* __restrict__ inst_plane,
+                                                       const int* __restrict__ task_slot, const int* __restrict__ task_x,
+                                                       const int* __restrict__ task_start, int* __restrict__ task_n,
+                                                       int* __restrict__ changes, int* __restrict__ spans, int ntasks, int H,
+                                                       int W, int write) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (slot >= total) return;
+  if (t >= ntasks) return;
+  const int slot = task_slot[t], x = task_x[t];
   const int plane = inst_plane[slot];
   const int lab = slot - offsets[plane] + 1;
   const int* g = geo + (long)slot * 5;
-  const int area = g[0];
+  const int rmin = g[1], rmax = g[2], cmax = g[4];
+  const bool full = (rmin == 0 && rmax == H - 1);
+  const int* L = labels + (long)plane * H * W;
+  int* dst = write ? changes + task_start[t] : nullptr;
+  uint32_t carry = (full && x > 0) ? (uint32_t)(__ldg(L + (long)(H - 1) * W + (x - 1)) == lab) : 0u;
   int n = 0;
-  int span = 0;
-  if (area > 0) {
-    const int rmin = g[1], rmax = g[2], cmin = g[3], cmax = g[4];
-    const int* L = labels + (long)plane * H * W;
-    int* dst = write ? changes + out_start[slot] : nullptr;
-    uint32_t carry = 0;        // mask value at the previous position of the column-major scan
-    for (int x = cmin; x <= cmax; ++x) {
-      // the pixels between the previous position walked and (rmin, x) are zeros unless the box spans the full height
-      if (carry && !(rmin == 0 && rmax == H - 1)) {
-        if (write && lane == 0) dst[n] = (x - 1) * H + rmax + 1;
-        ++n;
-        carry = 0;
-      }
-      for (int y0 = rmin; y0 <= rmax; y0 += 32) {
-        const int y = y0 + lane;
-        const bool on = (y <= rmax) && (__ldg(L + (long)y * W + x) == lab);
-        const uint32_t bits = __ballot_sync(0xffffffffu, on);
-        const int valid = min(32, rmax - y0 + 1);
-        const uint32_t vmask = valid == 32 ? 0xffffffffu : ((1u << valid) - 1u);
-        const uint32_t flips = (bits ^ ((bits << 1) | carry)) & vmask;
-        if (write && ((flips >> lane) & 1u)) dst[n + __popc(flips & ((1u << lane) - 1u))] = x * H + y;
-        // still on at the top of a column with the scan's previous pixel on (no gap: the box spans the full height):
-        // this run of ones started in an earlier column
-        if (y0 == rmin && carry && (bits & 1u)) span = 1;
-        n += __popc(flips);
-        carry = (bits >> (valid - 1)) & 1u;
-      }
-    }
-    // the scan continues after the box: zeros, unless the box ends at the very last pixel of the image
-    if (carry && !(cmax == W - 1 && rmax == H - 1)) {
-      if (write && lane == 0) dst[n] = cmax * H + rmax + 1;
+  for (int y0 = rmin; y0 <= rmax; y0 += 32) {
+    const int y = y0 + lane;
+    const bool on = (y <= rmax) && (__ldg(L + (long)y * W + x) == lab);
+    const uint32_t bits = __ballot_sync(0xffffffffu, on);
+    const int valid = min(32, rmax - y0 + 1);
+    const uint32_t vmask = valid == 32 ? 0xffffffffu : ((1u << valid) - 1u);
+    const uint32_t flips = (bits ^ ((bits << 1) | carry)) & vmask;
+    if (write && ((flips >> lane) & 1u)) dst[n + __popc(flips & ((1u << lane) - 1u))] = x * H + y;
+    // still on at the top of a column whose entry state is on: this run of ones started in an earlier column
+    if (write && y0 == rmin && carry && (bits & 1u) && lane == 0) spans[slot] = 1;
+    n += __popc(flips);
+    carry = (bits >> (valid - 1)) & 1u;
+  }
+  // a run still on at the bottom of the box: it ends right below unless the scan continues into the next column
+  // (full-height box, not the last column of the box) or the image ends here
+  if (carry) {
+    const bool continues = full && x < cmax;                 // the next column task sees it as its entry state
+    const bool image_end = (x == W - 1 && rmax == H - 1);
+    if (!continues && !image_end) {
+      if (write && lane == 0) dst[n] = x * H + rmax + 1;
       ++n;
     }
   }
-  if (lane == 0) {
-    if (!write) nchanges[slot] = n;
-    else spans[slot] = span;
-  }
+  if (!write && lane == 0) task_n[t] = n;
 }
 
 // counts from change positions: cnt[0] = p0, cnt[i] = p_i - p_{i-1}, cnt[n] = H*W - p_{n-1}  (n + 1 counts per instance;
@@ -361,16 +358,16 @@ extern "C" int mcb_instance_geometry(const int* labels, const void* prob, int pr
   return MCB_OK;
 }
 
-extern "C" int mcb_rle_walk(const int* labels, const int* offsets, const int* counts, const int* geo,
-                            const int* inst_plane, const int* out_start, int* nchanges, int* changes, int* spans,
-                            int total, int h, int w, int write, void* stream) {
-  MCB_REQUIRE(labels && offsets && counts && geo && inst_plane && nchanges, "rle_walk: null pointer");
-  MCB_REQUIRE(!write || (out_start && changes && spans), "rle_walk: write pass needs out_start, changes, spans");
+extern "C" int mcb_rle_walk(const int* labels, const int* offsets, const int* geo, const int* inst_plane,
+                            const int* task_slot, const int* task_x, const int* task_start, int* task_n, int* changes,
+                            int* spans, int ntasks, int h, int w, int write, void* stream) {
+  MCB_REQUIRE(labels && offsets && geo && inst_plane && task_slot && task_x && task_n, "rle_walk: null pointer");
+  MCB_REQUIRE(!write || (task_start && changes && spans), "rle_walk: write pass needs task_start, changes, spans");
   MCB_REQUIRE((long)h * w < (1L << 31), "rle_walk: plane too large");
-  if (total <= 0) return MCB_OK;
+  if (ntasks <= 0) return MCB_OK;
   const int warps_per_block = 4;
-  rle_walk_kernel<<<(total + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, ST>>>(
-      labels, offsets, counts, geo, inst_plane, out_start, nchanges, changes, spans, total, h, w, write);
+  rle_walk_kernel<<<(ntasks + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, ST>>>(
+      labels, offsets, geo, inst_plane, task_slot, task_x, task_start, task_n, changes, spans, ntasks, h, w, write);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

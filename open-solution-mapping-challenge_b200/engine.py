@@ -83,7 +83,7 @@ class Plan:
         mode = os.environ.get("MCB_SYNC_BN", "0")
         self.sync_bn = training and self.world > 1 and mode in ("1", "2")
         # MCB_SYNC_BN=2: the per-BatchNorm exchange is a one-shot all-reduce over NVLink peer memory (csrc/sync.cu) instead
-        # of a NCCL call: partial sums live in symmetric memory, global sums land in local buffers
+        # of a NCCL call: every rank pushes its partial sums into its peers' receive buffers (symmetric memory)
         self.sync_nvlink = self.sync_bn and mode == "2"
         self.bn_scale = self.world if self.sync_bn else 1
         if self.sync_nvlink:
@@ -98,8 +98,11 @@ class Plan:
                 ptrs = torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=self.dev)
                 self._keep.append(h)
                 return t, ptrs
-            self._stats_arena, self._peer_stats = sym(2 * total_c, F32)          # conv epilogues accumulate here
-            self._dstats_sym, self._peer_dstats = sym(2 * total_c, F32)          # [dbeta | dgamma] partial sums
+            # partial sums stay in LOCAL memory; every rank owns receive buffers [world][2 total_c] that its peers push into
+            self._dstats_loc = torch.zeros(2 * total_c, dtype=F32, device=self.dev)      # [dbeta | dgamma] partial sums
+            self._recv_stats, self._peer_recv_stats = sym(self.world * 2 * total_c, F32)
+            self._recv_dstats, self._peer_recv_dstats = sym(self.world * 2 * total_c, F32)
+            self._sync_stride = 2 * total_c
             self._flags_sym, self._peer_flags = sym(2 * n_bn * self.world, torch.int32)
             self._gstats = torch.zeros(2 * total_c, dtype=F32, device=self.dev)    # global [sum, sum^2]
             self._gdstats = torch.zeros(2 * total_c, dtype=F32, device=self.dev)   # global [dbeta | dgamma]
@@ -158,7 +161,7 @@ class Plan:
         if self.sync_nvlink:
             # the reduction kernels accumulate this rank's partial sums in symmetric memory; the exchange writes the
             # global sums to local buffers (what the normalisation passes read) and global / world to the gradient slots
-            b.dbeta, b.dgamma = self._dstats_sym[b.off:b.off + c], self._dstats_sym[b.off + c:b.off + 2 * c]
+            b.dbeta, b.dgamma = self._dstats_loc[b.off:b.off + c], self._dstats_loc[b.off + c:b.off + 2 * c]
             b.app_dbeta, b.app_dgamma = self._gdstats[b.off:b.off + c], self._gdstats[b.off + c:b.off + 2 * c]
             tr_stats = self._gstats[b.off:b.off + 2 * c]
         else:
@@ -217,8 +220,9 @@ class Plan:
         """SyncBN forward: sum the per-rank [sum, sum^2] before the BN apply pass reads them"""
         if self.sync_nvlink:
             F.add("bn_exchange", lambda: L.fcall(
-                "mcb_sync_exchange", self._peer_stats.data_ptr(), self._peer_flags.data_ptr(), self.rank, self.world,
-                bn.off, 2 * bn.c, bn.idx, self._sync_step.data_ptr(), self._gstats[bn.off:].data_ptr(), None, None, 0, 0.0))
+                "mcb_sync_exchange", self._stats_arena.data_ptr(), self._peer_recv_stats.data_ptr(),
+                self._peer_flags.data_ptr(), self.rank, self.world, self._sync_stride, bn.off, 2 * bn.c, bn.idx,
+                self._sync_step.data_ptr(), self._gstats[bn.off:].data_ptr(), None, None, 0, 0.0))
         elif self.sync_bn:
             F.add("bn_allreduce", lambda: dist.all_reduce(bn.stats))
 
@@ -228,8 +232,9 @@ class Plan:
         arena-wide gradient all-reduce adds the ranks up again)."""
         if self.sync_nvlink:
             B.add("bn_exchange", lambda: L.fcall(
-                "mcb_sync_exchange", self._peer_dstats.data_ptr(), self._peer_flags.data_ptr(), self.rank, self.world,
-                bn.off, 2 * bn.c, self._n_bn + bn.idx, self._sync_step.data_ptr(), self._gdstats[bn.off:].data_ptr(),
+                "mcb_sync_exchange", self._dstats_loc.data_ptr(), self._peer_recv_dstats.data_ptr(),
+                self._peer_flags.data_ptr(), self.rank, self.world, self._sync_stride, bn.off, 2 * bn.c,
+                self._n_bn + bn.idx, self._sync_step.data_ptr(), self._gdstats[bn.off:].data_ptr(),
                 bn.g32_dbeta.data_ptr(), bn.g32_dgamma.data_ptr(), bn.c, 1.0 / self.world))
         elif self.sync_bn:
             g32 = self.net._g32
@@ -532,7 +537,7 @@ class Plan:
         if first == 0:
             L.zero(self.net._g32)
             if self.sync_nvlink:
-                L.zero(self._dstats_sym)
+                L.zero(self._dstats_loc)
         # Weight/bias-gradient launches are leaves of the backward graph (they only add into the gradient arena): they
         # go to a side stream, forked after their producer and joined at the end, so the tensor-core-bound wgrad GEMMs
         # overlap the HBM-bound BatchNorm-backward kernels of the layers below instead of queueing behind them.

@@ -463,6 +463,7 @@ class FusedTrainStep:
         # pinned staging ring: a slot is rewritten only after the copy that last read it has executed
         self._hyper_ring = [(torch.zeros(3, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
         self._adam_cfg = None
+        self.phase_marks = None
 
     # segments ----------------------------------------------------------------------------------------------------
     def _seg_forward(self):
@@ -573,14 +574,24 @@ class FusedTrainStep:
             self._hyper.copy_(host, non_blocking=True)
             ev.record()
         first = self.graphs is None and self.use_graphs
+        marks = self.phase_marks            # bench.py: CUDA events at the phase boundaries of a step (None = off)
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
         if first or not self.use_graphs:
             self._seg_forward()
         else:
             self.graphs[0].replay()
+        mark("forward")
         finish_target()
         self._loss_partials()
         if self.world > 1:
             dist.all_reduce(self.sums)
+        mark("loss sums")
         eager = first or not self.use_graphs
         if self.segments is None:
             if eager:
@@ -613,8 +624,10 @@ class FusedTrainStep:
                     works.append(dist.all_reduce(grad_slice, async_op=True))
             for wk in works:
                 wk.wait()
+        mark("backward (+ in-graph Adam / all-reduce)")
         if not self.adam_in_graph:
             self._adam(lr, betas, eps, weight_decay)
+            mark("adam")
         if first:
             torch.cuda.synchronize()
             self._capture()

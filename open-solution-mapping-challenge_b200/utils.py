@@ -3,7 +3,7 @@ bounding_box_from_rle) on the GPU.
 
 The reference turns every labelled instance into a full-image uint8 mask on the host and hands it to pycocotools
 (`cocomask.encode` on the Fortran-ordered mask, `cocomask.toBbox`), twice per instance.  Here one device pass computes
-area / bounding box of every instance of a batch of label planes, one warp per instance run-length encodes its mask
+area / bounding box of every instance of a batch of label planes, one warp per (instance, column) run-length encodes the mask
 inside its bounding box (csrc/instances.cu), and only the run lengths come back to the host, where the LEB128-like
 COCO string of pycocotools' rleToString is produced with vectorised numpy.  No pycocotools, no CPU fallback for the
 pixel work.
@@ -81,18 +81,30 @@ def rle_encode_instances(labels, counts, geometry=None):
         return np.zeros(0, np.uint32), np.zeros(1, np.int64), np.zeros(0, bool), geo
     dev = labels.device
     inst_plane = torch.from_numpy(geo["plane"]).to(dev)
-    nchanges = torch.empty(total, dtype=torch.int32, device=dev)
-    L.fcall("mcb_rle_walk", labels.data_ptr(), geo["_offsets"].data_ptr(), geo["_counts"].data_ptr(),
-            geo["_geo"].data_ptr(), inst_plane.data_ptr(), None, nchanges.data_ptr(), None, None, total, h, w, 0)
-    n_h = nchanges.cpu().numpy().astype(np.int64)
+    # one task per (instance, bounding-box column): columns are independent, so the image-sized background instance of
+    # every plane is walked by 300 warps instead of one
+    width = np.where(geo["area"] > 0, geo["cmax"] - geo["cmin"] + 1, 0).astype(np.int64)
+    ntasks = int(width.sum())
+    task_slot_h = np.repeat(np.arange(total, dtype=np.int32), width)
+    first = np.concatenate([[0], np.cumsum(width)[:-1]])
+    task_x_h = (np.arange(ntasks, dtype=np.int64) - np.repeat(first, width) + np.repeat(geo["cmin"].astype(np.int64), width)).astype(np.int32)
+    task_slot, task_x = torch.from_numpy(task_slot_h).to(dev), torch.from_numpy(task_x_h).to(dev)
+    task_n = torch.zeros(max(ntasks, 1), dtype=torch.int32, device=dev)
+    L.fcall("mcb_rle_walk", labels.data_ptr(), geo["_offsets"].data_ptr(), geo["_geo"].data_ptr(), inst_plane.data_ptr(),
+            task_slot.data_ptr(), task_x.data_ptr(), None, task_n.data_ptr(), None, None, ntasks, h, w, 0)
+    task_n_h = task_n[:ntasks].cpu().numpy().astype(np.int64)
+    task_start_h = np.concatenate([[0], np.cumsum(task_n_h)[:-1]]).astype(np.int32) if ntasks else np.zeros(0, np.int32)
+    n_changes_total = int(task_n_h.sum())
+    n_h = np.bincount(task_slot_h, weights=task_n_h, minlength=total).astype(np.int64)      # changes per instance
     out_start_h = np.concatenate([[0], np.cumsum(n_h)[:-1]]).astype(np.int32)
-    n_changes_total = int(n_h.sum())
+    task_start = torch.from_numpy(task_start_h).to(dev)
+    nchanges = torch.from_numpy(n_h.astype(np.int32)).to(dev)
     out_start = torch.from_numpy(out_start_h).to(dev)
     changes = torch.empty(max(n_changes_total, 1), dtype=torch.int32, device=dev)
     spans = torch.zeros(total, dtype=torch.int32, device=dev)
-    L.fcall("mcb_rle_walk", labels.data_ptr(), geo["_offsets"].data_ptr(), geo["_counts"].data_ptr(),
-            geo["_geo"].data_ptr(), inst_plane.data_ptr(), out_start.data_ptr(), nchanges.data_ptr(),
-            changes.data_ptr(), spans.data_ptr(), total, h, w, 1)
+    L.fcall("mcb_rle_walk", labels.data_ptr(), geo["_offsets"].data_ptr(), geo["_geo"].data_ptr(), inst_plane.data_ptr(),
+            task_slot.data_ptr(), task_x.data_ptr(), task_start.data_ptr(), task_n.data_ptr(), changes.data_ptr(),
+            spans.data_ptr(), ntasks, h, w, 1)
     total_counts = n_changes_total + total
     slot_of_count = torch.from_numpy(np.repeat(np.arange(total, dtype=np.int32), n_h + 1)).to(dev)
     cnts = torch.empty(total_counts, dtype=torch.int32, device=dev)
