@@ -352,19 +352,42 @@ int mcb_target_channels(const uint8_t* mask, const void* dist_f16, const long lo
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Synchronised BatchNorm over NVLink peer memory (SURVEY.md 8e collective (2)): one-shot all-reduce of a small fp32
- * vector.  `partial` = this rank's partial sums (local memory, [stride] floats, this exchange at [offset, offset+count)).
- * peer_recv / peer_flags: DEVICE arrays of `world` pointers, entry r = rank r's symmetric buffer as mapped in this
- * process (caller's plumbing, e.g. torch symmetric memory): recv fp32 [world][stride] per rank, flags uint32
- * [exchanges][world] per rank, zeroed once.  The kernel pushes partial[offset..] into slot [rank] of every peer's recv,
- * stamps the flags, waits for the peers' stamps and writes out[c] = sum over ranks (in rank order); optionally
- * out2_first[c] / out2_second[c - split] = scale2 * out[c].  `exchange` numbers the exchange inside a step, *step is the
- * device-resident step stamp (mcb_sync_step_bump at the start of every step).  count, offset, stride multiples of 4.
+ * vector.  `partial` = this rank's partial sums (local memory, this exchange at [offset, offset+count)).  peer_recv:
+ * DEVICE array of `world` pointers, entry r = rank r's symmetric receive buffer as mapped in this process (caller's
+ * plumbing, e.g. torch symmetric memory): per rank [world][stride] pairs of (fp32 value, uint32 stamp), zeroed once.
+ * The kernel pushes (partial[offset + c], *step) into slot [rank] of every peer, polls its own slots for this step's
+ * stamp and writes out[c] = sum over ranks (in rank order); optionally out2_first[c] / out2_second[c - split] =
+ * scale2 * out[c].  *step is the device-resident step stamp (mcb_sync_step_bump at the start of every step; never 0).
  * Asynchronous on `stream`, capturable.
  * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* partial;     /* this rank's partial sums (local memory) */
+  void* const* peer_recv;   /* device array [world]; NULL = plain (unsynchronised) launch */
+  int rank, world;
+  long stride, offset;
+  int count;
+  const unsigned* step;
+  float* out;               /* global sums */
+  float* out2_first;        /* optional scaled copies */
+  float* out2_second;
+  int split;
+  float scale2;
+  unsigned* ready;          /* one uint32 per exchange: the consuming kernel's block 0 publishes *step here */
+} mcb_sync_desc;
 int mcb_sync_step_bump(unsigned* step, void* stream);
-int mcb_sync_exchange(const float* partial, float* const* peer_recv, unsigned* const* peer_flags, int rank, int world,
-                      long stride, long offset, int count, int exchange, const unsigned* step, float* out,
-                      float* out2_first, float* out2_second, int split, float scale2, void* stream);
+int mcb_sync_exchange(const float* partial, void* const* peer_recv, int rank, int world, long stride, long offset,
+                      int count, const unsigned* step, float* out, float* out2_first, float* out2_second, int split,
+                      float scale2, void* stream);
+
+/* the same exchange run INSIDE the kernel that consumes the sums (block 0 exchanges and publishes desc->ready, the other
+ * blocks wait on it): mcb_bn_train_apply_global / mcb_bn_bwd_apply_global with sync descriptors (bn->stats, resp.
+ * dbeta / dgamma, must point at desc->out).  NULL descriptors = the plain kernels. */
+int mcb_bn_train_apply_sync(const void* z, const mcb_bn_train* bn, const void* residual, const mcb_bn_train* res_bn,
+                            int relu, void* y, long pixels, long stat_count, int c, float momentum, float eps,
+                            const mcb_sync_desc* sync, const mcb_sync_desc* res_sync, void* stream);
+int mcb_bn_bwd_apply_sync(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
+                          const float* gamma, const float* dbeta, const float* dgamma, void* dz, void* g_out,
+                          int g_accumulate, long pixels, long stat_count, int c, const mcb_sync_desc* sync, void* stream);
 
 #ifdef __cplusplus
 }

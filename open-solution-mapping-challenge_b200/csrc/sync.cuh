@@ -1,0 +1,106 @@
+// sync.cuh — device side of the one-shot NVLink exchange (see sync.cu for the protocol), shared by the stand-alone
+// exchange kernel and by the BatchNorm kernels that run the exchange in their own prologue.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcb {
+
+constexpr int kMaxWorld = 16;
+
+struct SyncDesc {
+  const float* partial;      // this rank's partial sums (local)
+  float2* const* recv;       // device array [world]: rank r's receive buffer as mapped here; nullptr = no exchange
+  int rank, world;
+  long stride, offset;
+  int count;
+  const unsigned* step;      // device-resident step stamp
+  float* out;                // global sums (local memory)
+  float* out2a;              // optional scaled copies: [0, split) -> out2a, [split, count) -> out2b
+  float* out2b;
+  int split;
+  float scale2;
+  unsigned* ready;           // fused form only: set to *step once `out` is complete (one word per exchange)
+};
+
+__device__ __forceinline__ void st_pair(float2* p, float v, unsigned stamp) {
+  asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v), "f"(__uint_as_float(stamp)) : "memory");
+}
+__device__ __forceinline__ float2 ld_pair(const float2* p) {
+  float2 v;
+  asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+// executed by ALL threads of the calling block
+__device__ __forceinline__ void sync_exchange_block(const SyncDesc& d) {
+  const unsigned step = *d.step;
+  const int t = threadIdx.x, nt = blockDim.x;
+  // 1. push stamped pairs to every peer
+  for (int c = t; c < d.count; c += nt) {
+    const float v = d.partial[d.offset + c];
+    for (int p = 0; p < d.world; ++p) {
+      if (p == d.rank) continue;
+      st_pair(d.recv[p] + (long)d.rank * d.stride + d.offset + c, v, step);
+    }
+  }
+  // 2. poll own slots, 3. reduce in rank order.  All peers' pairs of an element are requested before the first stamp
+  //    is examined (independent loads in flight); only pairs that have not landed yet are polled again.
+  const float2* mine = d.recv[d.rank];
+  for (int c = t; c < d.count; c += nt) {
+    float2 v[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < d.world && r != d.rank) v[r] = ld_pair(mine + (long)r * d.stride + d.offset + c);
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r) {
+      if (r >= d.world) break;
+      if (r == d.rank) {
+        s += d.partial[d.offset + c];
+        continue;
+      }
+      // bounded spin (~10 s): a peer that never arrives (crashed rank, mismatched plans) must surface as a CUDA error
+      // on this rank, not as a silent hang of the whole job
+      long spins = 0;
+      while (__float_as_uint(v[r].y) != step) {
+        if (++spins > (1L << 25)) __trap();
+        v[r] = ld_pair(mine + (long)r * d.stride + d.offset + c);
+      }
+      s += v[r].x;
+    }
+    d.out[c] = s;
+    if (d.out2a != nullptr) {
+      if (c < d.split) d.out2a[c] = s * d.scale2;
+      else d.out2b[c - d.split] = s * d.scale2;
+    }
+  }
+}
+
+// Prologue of a kernel that CONSUMES the global sums: block 0 runs the exchange(s) and publishes `ready`, every other
+// block waits for it.  Block 0 is dispatched with the first wave, and it waits only for other GPUs, never for blocks of
+// its own grid, so the gate cannot deadlock whatever the residency of the grid.  Consumers must read `out` with
+// L2-coherent loads (__ldcg), not through the read-only path.
+__device__ __forceinline__ void sync_gate(const SyncDesc& a, const SyncDesc& b) {
+  if (a.recv == nullptr) return;
+  const unsigned step = *a.step;
+  if (blockIdx.x == 0) {
+    sync_exchange_block(a);
+    if (b.recv != nullptr) sync_exchange_block(b);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.ready), "r"(step) : "memory");
+  } else {
+    if (threadIdx.x == 0) {
+      unsigned v;
+      long spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.ready) : "memory");
+        if (++spins > (1L << 27)) __trap();
+      } while (v != step);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mcb
