@@ -701,14 +701,16 @@ def main():
     }
     # DRAM traffic of the GEMM family over one step, from the committed ncu capture of this same workload (a number
     # taken under the profiler is evidence, not a bench value): compare with the family's algorithmic bytes
-    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_gemm_traffic.json")
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_gemm_traffic.json")
+    if not os.path.exists(tj):
+        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_gemm_traffic.json")
     if (args.encoder, args.batch, args.size) == (101, 32, 320) and os.path.exists(tj):
         with open(tj) as f:
             tr = json.load(f)
         line["roofline"]["traffic"] = int(tr["dram_bytes"])
         line["roofline"]["traffic_unit"] = "DRAM bytes per step per GPU, summed over the family's %d launches " \
                                            "(ncu dram__bytes_read.sum + dram__bytes_write.sum, cold-cache replay)" % tr["launches"]
-        line["roofline"]["traffic_source"] = "profiles/r01c_gemm_traffic.json"
+        line["roofline"]["traffic_source"] = "profiles/" + os.path.basename(tj)
     if not args.no_breakdown:
         bd, total = breakdown(fused)
         note("breakdown done")

@@ -336,6 +336,13 @@ int mcb_contour_length(const int* labels, const int* offsets, const int* counts,
  * [n][3][h + 2 pad_h][w + 2 pad_w]; mean3 / std3 are HOST pointers to three floats; bit-exact fp32 */
 int mcb_image_pad_normalize(const uint8_t* img, float* out, int n, int h, int w, int pad_h, int pad_w, int pad_mode,
                             const float* mean3, const float* std3, void* stream);
+/* transforms.Resize on a PIL image (src/loaders.py:287-305, loader_mode 'resize') = Pillow ImagingResample, BILINEAR,
+ * 8 bits per channel: horizontal pass into tmp uint8 [n][h][out_w][c], vertical pass into out uint8 [n][out_h][out_w][c];
+ * coef_* int32 [out][ksize] = Pillow's 22-bit fixed-point filter rows, bounds_* int32 [out][2] = (first tap, taps),
+ * computed by the caller like precompute_coeffs / normalize_coeffs_8bpc (mcb200.preparation does); bit-exact */
+int mcb_pil_resize_bilinear_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, const int* coef_h, const int* bounds_h,
+                               int ksize_h, const int* coef_v, const int* bounds_v, int ksize_v, int n, int h, int w,
+                               int c, int out_h, int out_w, void* stream);
 /* update_distances + clean_distances (src/preparation.py:151-168): masks uint8 [k][h][w] (one plane per building of ONE
  * image, non-empty); dist_sum fp16 [h][w] = d_nearest + d_second (one building counts twice, none gives 0),
  * second_nearest fp64 [h][w]; distances are scipy.ndimage.distance_transform_edt(1 - mask), exact;
@@ -360,34 +367,10 @@ int mcb_target_channels(const uint8_t* mask, const void* dist_f16, const long lo
  * scale2 * out[c].  *step is the device-resident step stamp (mcb_sync_step_bump at the start of every step; never 0).
  * Asynchronous on `stream`, capturable.
  * ---------------------------------------------------------------------------------------------------------------- */
-typedef struct {
-  const float* partial;     /* this rank's partial sums (local memory) */
-  void* const* peer_recv;   /* device array [world]; NULL = plain (unsynchronised) launch */
-  int rank, world;
-  long stride, offset;
-  int count;
-  const unsigned* step;
-  float* out;               /* global sums */
-  float* out2_first;        /* optional scaled copies */
-  float* out2_second;
-  int split;
-  float scale2;
-  unsigned* ready;          /* one uint32 per exchange: the consuming kernel's block 0 publishes *step here */
-} mcb_sync_desc;
 int mcb_sync_step_bump(unsigned* step, void* stream);
 int mcb_sync_exchange(const float* partial, void* const* peer_recv, int rank, int world, long stride, long offset,
                       int count, const unsigned* step, float* out, float* out2_first, float* out2_second, int split,
                       float scale2, void* stream);
-
-/* the same exchange run INSIDE the kernel that consumes the sums (block 0 exchanges and publishes desc->ready, the other
- * blocks wait on it): mcb_bn_train_apply_global / mcb_bn_bwd_apply_global with sync descriptors (bn->stats, resp.
- * dbeta / dgamma, must point at desc->out).  NULL descriptors = the plain kernels. */
-int mcb_bn_train_apply_sync(const void* z, const mcb_bn_train* bn, const void* residual, const mcb_bn_train* res_bn,
-                            int relu, void* y, long pixels, long stat_count, int c, float momentum, float eps,
-                            const mcb_sync_desc* sync, const mcb_sync_desc* res_sync, void* stream);
-int mcb_bn_bwd_apply_sync(const void* dy, const void* y_mask, const void* z, const float* mean, const float* invstd,
-                          const float* gamma, const float* dbeta, const float* dgamma, void* dz, void* g_out,
-                          int g_accumulate, long pixels, long stat_count, int c, const mcb_sync_desc* sync, void* stream);
 
 #ifdef __cplusplus
 }

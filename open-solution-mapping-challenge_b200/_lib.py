@@ -186,6 +186,7 @@ def zero(t):
 _SIGS5 = {
     "mcb_image_pad_normalize": [vp, vp, ci, ci, ci, ci, ci, ci, fp, fp, vp],
     "mcb_edt_two_nearest": [vp, ci, ci, ci, vp, vp, vp, vp],
+    "mcb_pil_resize_bilinear_u8": [vp, vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp],
     "mcb_size_matrix": [vp, vp, vp, ci, ci, vp],
     "mcb_target_channels": [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
 }
@@ -198,16 +199,3 @@ lib.mcb_sync_step_bump.restype = ci
 lib.mcb_sync_exchange.argtypes = [vp, vp, ci, ci, cl, cl, ci, vp, vp, vp, vp, ci, cf, vp]
 lib.mcb_sync_exchange.restype = ci
 
-
-class SyncDesc(C.Structure):
-    """mcb_sync_desc (include/mcb200.h): one synchronised-BatchNorm exchange run inside the consuming kernel"""
-    _fields_ = [("partial", vp), ("peer_recv", vp), ("rank", ci), ("world", ci), ("stride", cl), ("offset", cl),
-                ("count", ci), ("step", vp), ("out", vp), ("out2_first", vp), ("out2_second", vp), ("split", ci),
-                ("scale2", cf), ("ready", vp)]
-
-
-lib.mcb_bn_train_apply_sync.argtypes = [vp, C.POINTER(BNTrain), vp, C.POINTER(BNTrain), ci, vp, cl, cl, ci, cf, cf,
-                                        C.POINTER(SyncDesc), C.POINTER(SyncDesc), vp]
-lib.mcb_bn_train_apply_sync.restype = ci
-lib.mcb_bn_bwd_apply_sync.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, cl, cl, ci, C.POINTER(SyncDesc), vp]
-lib.mcb_bn_bwd_apply_sync.restype = ci

@@ -2,7 +2,6 @@
 // forward/backward), 2x2 max-pool, per-channel sums, the final 1x1 classifier, fused Adam.
 // All NHWC bf16 kernels move 16 bytes (8 channels) per thread per access; grids are sized in multiples of the SM count.
 #include "host_common.h"
-#include "sync.cuh"
 #include "../../include/mcb200.h"
 #include <algorithm>
 #include <math.h>
@@ -255,9 +254,8 @@ __device__ __forceinline__ void bn_train_coef(const BNTrain& b, int C, int c0, f
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    // (L2-coherent loads: in the synchronised form block 0 of THIS launch has just written the global sums)
-    const float mean = __ldcg(b.stats + c) / count;
-    const float var = fmaxf(__ldcg(b.stats + C + c) / count - mean * mean, 0.f);
+    const float mean = __ldg(b.stats + c) / count;
+    const float var = fmaxf(__ldg(b.stats + C + c) / count - mean * mean, 0.f);
     const float invstd = rsqrtf(var + eps);
     sc[j] = __ldg(b.gamma + c) * invstd;
     sh[j] = __ldg(b.beta + c) - mean * sc[j];
@@ -276,9 +274,8 @@ template <int RES>
 __global__ void __launch_bounds__(256) bn_train_apply_kernel(const uint4* __restrict__ z, BNTrain bn,
                                                              const uint4* __restrict__ r, BNTrain rbn, int relu,
                                                              uint4* __restrict__ y, long total8, int C8, float count,
-                                                             float eps, float momentum, SyncDesc sa, SyncDesc sb) {
+                                                             float eps, float momentum) {
   mcb::pdl_prologue();
-  sync_gate(sa, sb);   // synchronised BatchNorm: the one-shot NVLink exchange of [sum, sum^2] runs here (block 0)
   const long stride = (long)gridDim.x * blockDim.x;
   long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int c0 = (int)(i % C8) * 8;
@@ -415,12 +412,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ dbeta, const float* __restrict__ dgamma,
                                                            float inv_count, uint4* __restrict__ dz, uint4* __restrict__ g_out,
-                                                           long total8, int C8, SyncDesc sa) {
+                                                           long total8, int C8) {
   mcb::pdl_prologue();
-  {
-    SyncDesc none{};
-    sync_gate(sa, none);   // synchronised BatchNorm: the exchange of [dbeta | dgamma] runs here (block 0)
-  }
   const long stride = (long)gridDim.x * blockDim.x;
   long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int c0 = (int)(i % C8) * 8;
@@ -430,8 +423,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     mu[j] = __ldg(mean + c0 + j);
     is[j] = __ldg(invstd + c0 + j);
     a[j] = __ldg(gamma + c0 + j) * is[j];
-    k1[j] = __ldcg(dbeta + c0 + j) * inv_count;
-    k2[j] = __ldcg(dgamma + c0 + j) * inv_count;
+    k1[j] = __ldg(dbeta + c0 + j) * inv_count;
+    k2[j] = __ldg(dgamma + c0 + j) * inv_count;
   }
   for (; i < total8; i += 2 * stride) {
     const long idx[2] = {i, i + stride};
@@ -750,40 +743,13 @@ extern "C" int mcb_bn_train_apply(const void* z, const mcb_bn_train* bn, const v
                                   float eps, void* stream) {
   return mcb_bn_train_apply_global(z, bn, residual, res_bn, relu, y, pixels, pixels, c, momentum, eps, stream);
 }
-static SyncDesc to_desc(const mcb_sync_desc* d) {
-  SyncDesc s{};
-  if (d == nullptr || d->peer_recv == nullptr) return s;
-  s.partial = d->partial; s.recv = reinterpret_cast<float2* const*>(d->peer_recv); s.rank = d->rank; s.world = d->world;
-  s.stride = d->stride; s.offset = d->offset; s.count = d->count; s.step = d->step; s.out = d->out;
-  s.out2a = d->out2_first; s.out2b = d->out2_second; s.split = d->split; s.scale2 = d->scale2; s.ready = d->ready;
-  return s;
-}
-static int check_desc(const mcb_sync_desc* d, const char* what) {
-  if (d == nullptr || d->peer_recv == nullptr) return MCB_OK;
-  MCB_REQUIRE(d->partial && d->step && d->out && d->ready, "%s: sync descriptor with null pointer", what);
-  MCB_REQUIRE(d->world >= 1 && d->world <= kMaxWorld && d->rank >= 0 && d->rank < d->world && d->count > 0,
-              "%s: sync descriptor rank / world / count", what);
-  return MCB_OK;
-}
-
 extern "C" int mcb_bn_train_apply_global(const void* z, const mcb_bn_train* bn, const void* residual,
                                          const mcb_bn_train* res_bn, int relu, void* y, long pixels, long stat_count,
                                          int c, float momentum, float eps, void* stream) {
-  return mcb_bn_train_apply_sync(z, bn, residual, res_bn, relu, y, pixels, stat_count, c, momentum, eps, nullptr, nullptr,
-                                 stream);
-}
-extern "C" int mcb_bn_train_apply_sync(const void* z, const mcb_bn_train* bn, const void* residual,
-                                       const mcb_bn_train* res_bn, int relu, void* y, long pixels, long stat_count, int c,
-                                       float momentum, float eps, const mcb_sync_desc* sync, const mcb_sync_desc* res_sync,
-                                       void* stream) {
   MCB_REQUIRE(stat_count >= pixels, "bn_train_apply: stat_count %ld < pixels %ld", stat_count, pixels);
   MCB_REQUIRE(z && bn && y && bn->stats && bn->gamma && bn->beta && bn->mean && bn->invstd, "bn_train_apply: null pointer");
   MCB_REQUIRE(c % 8 == 0 && 256 % (c / 8) == 0, "bn_train_apply: channels %d (c/8 must divide 256)", c);
   MCB_REQUIRE(!(res_bn && !residual), "bn_train_apply: res_bn without residual");
-  MCB_REQUIRE(!(res_sync && res_sync->peer_recv && !(sync && sync->peer_recv)), "bn_train_apply: res_sync without sync");
-  if (int r = check_desc(sync, "bn_train_apply")) return r;
-  if (int r = check_desc(res_sync, "bn_train_apply")) return r;
-  const SyncDesc sa = to_desc(sync), sb = to_desc(res_sync);
   const long total8 = pixels * (c / 8);
   const int grid = grid_for((total8 + 1) / 2, 256);
   BNTrain b{bn->stats, bn->gamma, bn->beta, bn->running_mean, bn->running_var, bn->mean, bn->invstd};
@@ -792,11 +758,11 @@ extern "C" int mcb_bn_train_apply_sync(const void* z, const mcb_bn_train* bn, co
                            res_bn->mean, res_bn->invstd};
   const float count = (float)stat_count;
   if (residual == nullptr)
-    launch_pdl(bn_train_apply_kernel<0>, grid, 256, 0, ST, (const uint4*)z, b, nullptr, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum, sa, sb);
+    launch_pdl(bn_train_apply_kernel<0>, grid, 256, 0, ST, (const uint4*)z, b, nullptr, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
   else if (res_bn == nullptr)
-    launch_pdl(bn_train_apply_kernel<1>, grid, 256, 0, ST, (const uint4*)z, b, (const uint4*)residual, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum, sa, sb);
+    launch_pdl(bn_train_apply_kernel<1>, grid, 256, 0, ST, (const uint4*)z, b, (const uint4*)residual, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
   else
-    launch_pdl(bn_train_apply_kernel<2>, grid, 256, 0, ST, (const uint4*)z, b, (const uint4*)residual, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum, sa, sb);
+    launch_pdl(bn_train_apply_kernel<2>, grid, 256, 0, ST, (const uint4*)z, b, (const uint4*)residual, rb, relu, (uint4*)y, total8, c / 8, count, eps, momentum);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }
@@ -841,26 +807,17 @@ extern "C" int mcb_bn_bwd_apply_global(const void* dy, const void* y_mask, const
                                        const float* invstd, const float* gamma, const float* dbeta, const float* dgamma,
                                        void* dz, void* g_out, int g_accumulate, long pixels, long stat_count, int c,
                                        void* stream) {
-  return mcb_bn_bwd_apply_sync(dy, y_mask, z, mean, invstd, gamma, dbeta, dgamma, dz, g_out, g_accumulate, pixels, stat_count,
-                               c, nullptr, stream);
-}
-extern "C" int mcb_bn_bwd_apply_sync(const void* dy, const void* y_mask, const void* z, const float* mean,
-                                     const float* invstd, const float* gamma, const float* dbeta, const float* dgamma,
-                                     void* dz, void* g_out, int g_accumulate, long pixels, long stat_count, int c,
-                                     const mcb_sync_desc* sync, void* stream) {
   MCB_REQUIRE(stat_count >= pixels, "bn_bwd_apply: stat_count %ld < pixels %ld", stat_count, pixels);
   MCB_REQUIRE(dy && z && mean && invstd && gamma && dbeta && dgamma && dz, "bn_bwd_apply: null pointer");
   MCB_REQUIRE(c % 8 == 0, "bn_bwd_apply: channels %d", c);
   MCB_REQUIRE(256 % (c / 8) == 0, "bn_bwd_apply: channels %d (c/8 must divide 256)", c);
-  if (int r = check_desc(sync, "bn_bwd_apply")) return r;
-  const SyncDesc sa = to_desc(sync);
   const long total8 = pixels * (c / 8);
   const int grid = grid_for((total8 + 1) / 2, 256);
   const float ic = 1.0f / (float)stat_count;
 #define MCB_BWD(MASK, GOUT)                                                                                         \
   launch_pdl(bn_bwd_apply_kernel<MASK, GOUT>, grid, 256, 0, ST, (const uint4*)dy, (const uint4*)y_mask, (const uint4*)z, mean, \
                                                         invstd, gamma, dbeta, dgamma, ic, (uint4*)dz, (uint4*)g_out,  \
-                                                        total8, c / 8, sa)
+                                                        total8, c / 8)
   const int gout = g_out == nullptr ? 0 : (g_accumulate ? 2 : 1);
   if (y_mask != nullptr) {
     if (gout == 0) MCB_BWD(true, 0); else if (gout == 1) MCB_BWD(true, 1); else MCB_BWD(true, 2);

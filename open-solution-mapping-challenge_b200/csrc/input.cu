@@ -40,6 +40,54 @@ __global__ void pad_normalize_kernel(const uint8_t* __restrict__ img, float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------ PIL bilinear resize (8 bpc)
+// transforms.Resize((h, w)) on a PIL image (src/loaders.py:287-305, the `resize` loader mode -- neptune.yaml's default)
+// = Image.resize(BILINEAR) = Pillow's ImagingResample: a horizontal pass into an 8-bit temporary, then a vertical
+// pass, each output = clip8((2^21 + sum_k pixel_k * coef_k) >> 22) with per-output-index integer coefficient rows
+// (triangle filter widened by the scale factor when shrinking, normalised, rounded to 22 fractional bits -- computed
+// on the host in double precision exactly like Pillow's precompute_coeffs / normalize_coeffs_8bpc).  Integer
+// arithmetic throughout -> bit-exact.  coef int32 [out][ksize], bounds int32 [out][2] = (first source index, taps).
+constexpr int kPilPrecision = 32 - 8 - 2;
+__device__ __forceinline__ uint8_t pil_clip8(int v) {
+  v >>= kPilPrecision;
+  return (uint8_t)min(max(v, 0), 255);
+}
+// in [n][H][W][C] -> tmp [n][H][Wo][C]
+__global__ void pil_resize_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ tmp, const int* __restrict__ coef,
+                                    const int* __restrict__ bounds, int ksize, int H, int W, int Wo, int C) {
+  const int n = blockIdx.y;
+  const long total = (long)H * Wo * C;
+  const uint8_t* src = in + (long)n * H * W * C;
+  uint8_t* dst = tmp + (long)n * total;
+  for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+    const int c = q % C;
+    const int xx = (q / C) % Wo;
+    const int y = q / ((long)C * Wo);
+    const int x0 = bounds[2 * xx], taps = bounds[2 * xx + 1];
+    const int* k = coef + (long)xx * ksize;
+    int acc = 1 << (kPilPrecision - 1);
+    for (int t = 0; t < taps; ++t) acc += (int)src[((long)y * W + x0 + t) * C + c] * k[t];
+    dst[q] = pil_clip8(acc);
+  }
+}
+// tmp [n][H][Wo][C] -> out [n][Ho][Wo][C]
+__global__ void pil_resize_v_kernel(const uint8_t* __restrict__ tmp, uint8_t* __restrict__ out, const int* __restrict__ coef,
+                                    const int* __restrict__ bounds, int ksize, int H, int Ho, int Wo, int C) {
+  const int n = blockIdx.y;
+  const long row = (long)Wo * C, total = (long)Ho * row;
+  const uint8_t* src = tmp + (long)n * H * row;
+  uint8_t* dst = out + (long)n * total;
+  for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+    const int yy = q / row;
+    const long r = q % row;
+    const int y0 = bounds[2 * yy], taps = bounds[2 * yy + 1];
+    const int* k = coef + (long)yy * ksize;
+    int acc = 1 << (kPilPrecision - 1);
+    for (int t = 0; t < taps; ++t) acc += (int)src[(long)(y0 + t) * row + r] * k[t];
+    dst[q] = pil_clip8(acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ exact EDT, two nearest
 // scipy.ndimage.distance_transform_edt(1 - mask): Euclidean distance of every pixel to the nearest pixel of the
 // instance, sqrt of the exact integer squared distance in float64.
@@ -151,6 +199,19 @@ extern "C" int mcb_image_pad_normalize(const uint8_t* img, float* out, int n, in
   MCB_REQUIRE(pad_mode == 0 || pad_mode == 1, "pad_normalize: pad_mode %d (0 replicate, 1 reflect-101)", pad_mode);
   pad_normalize_kernel<<<grid_in((long)(h + 2 * pad_h) * (w + 2 * pad_w), n, 256), 256, 0, ST>>>(
       img, out, h, w, pad_h, pad_w, pad_mode, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  MCB_LAUNCH_CHECK();
+  return MCB_OK;
+}
+
+extern "C" int mcb_pil_resize_bilinear_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, const int* coef_h,
+                                          const int* bounds_h, int ksize_h, const int* coef_v, const int* bounds_v,
+                                          int ksize_v, int n, int h, int w, int c, int out_h, int out_w, void* stream) {
+  MCB_REQUIRE(in && tmp && out && coef_h && bounds_h && coef_v && bounds_v, "pil_resize: null pointer");
+  MCB_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && out_h > 0 && out_w > 0 && ksize_h > 0 && ksize_v > 0, "pil_resize: bad shape");
+  pil_resize_h_kernel<<<grid_in((long)h * out_w * c, n, 256), 256, 0, ST>>>(in, tmp, coef_h, bounds_h, ksize_h, h, w, out_w, c);
+  MCB_LAUNCH_CHECK();
+  pil_resize_v_kernel<<<grid_in((long)out_h * out_w * c, n, 256), 256, 0, ST>>>(tmp, out, coef_v, bounds_v, ksize_v, h, out_h,
+                                                                             out_w, c);
   MCB_LAUNCH_CHECK();
   return MCB_OK;
 }

@@ -46,7 +46,7 @@ extern "C" int mcb_sync_exchange(const float* partial, void* const* peer_recv, i
   MCB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && count > 0, "sync_exchange: bad rank / world / count");
   MCB_REQUIRE((out2_first == nullptr) == (out2_second == nullptr) && split >= 0 && split <= count, "sync_exchange: bad split");
   SyncDesc d{partial, reinterpret_cast<float2* const*>(peer_recv), rank, world, stride, offset, count, step, out, out2_first,
-             out2_second, split, scale2, nullptr};
+             out2_second, split, scale2};
   sync_exchange_kernel<<<1, kSyncThreads, 0, static_cast<cudaStream_t>(stream)>>>(d);
   MCB_LAUNCH_CHECK();
   return MCB_OK;

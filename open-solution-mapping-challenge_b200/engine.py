@@ -53,7 +53,7 @@ class _OpList(list):
 class _BN:
     """per-BatchNorm device state"""
     __slots__ = ("mod", "c", "stats", "scale", "shift", "mean", "invstd", "gamma", "beta", "dgamma", "dbeta", "tr",
-                 "idx", "off", "app_dgamma", "app_dbeta", "g32_dgamma", "g32_dbeta", "sync_fwd", "sync_bwd")
+                 "idx", "off", "app_dgamma", "app_dbeta", "g32_dgamma", "g32_dbeta")
 
 
 class Plan:
@@ -108,10 +108,6 @@ class Plan:
             self._gdstats = torch.zeros(2 * total_c, dtype=F32, device=self.dev)   # global [dbeta | dgamma]
             self._sync_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
             self._n_bn = n_bn
-            # MCB_SYNC_FUSED=1 (default): the exchange runs in the prologue of the kernel that consumes the sums (block 0
-            # exchanges, the others wait on a ready word) instead of a launch of its own
-            self.sync_fused = os.environ.get("MCB_SYNC_FUSED", "1") == "1"
-            self._sync_ready = torch.zeros(2 * n_bn, dtype=torch.int32, device=self.dev)
             torch.cuda.synchronize()
             dist.barrier()
         self.bias_sum = {}         # id(conv+bias+ReLU output) -> its bias-gradient vector (fused into the consumer's dgrad)
@@ -174,21 +170,6 @@ class Plan:
             tr_stats = b.stats
         b.tr = ops.make_bn_train(tr_stats, b.gamma, b.beta, mod.running_mean, mod.running_var, b.mean, b.invstd) \
             if self.training else None
-        b.sync_fwd = b.sync_bwd = None
-        if self.sync_nvlink and self.sync_fused:
-            def desc(partial, peer_recv, out, ready_idx, out2a=None, out2b=None, split=0, scale2=0.0):
-                d = L.SyncDesc()
-                d.partial, d.peer_recv, d.rank, d.world = partial.data_ptr(), peer_recv.data_ptr(), self.rank, self.world
-                d.stride, d.offset, d.count, d.step = self._sync_stride, b.off, 2 * c, self._sync_step.data_ptr()
-                d.out = out[b.off:].data_ptr()
-                d.out2_first = out2a.data_ptr() if out2a is not None else None
-                d.out2_second = out2b.data_ptr() if out2b is not None else None
-                d.split, d.scale2 = split, scale2
-                d.ready = self._sync_ready[ready_idx:].data_ptr()
-                return d
-            b.sync_fwd = desc(self._stats_arena, self._peer_recv_stats, self._gstats, b.idx)
-            b.sync_bwd = desc(self._dstats_loc, self._peer_recv_dstats, self._gdstats, self._n_bn + b.idx, b.g32_dbeta,
-                              b.g32_dgamma, c, 1.0 / self.world)
         self._bns.append(b)
         return b
 
@@ -227,9 +208,8 @@ class Plan:
         F = self.fwd_ops
         if self.training:
             rtr = res_bn.tr if res_bn is not None else None
-            rsync = res_bn.sync_fwd if res_bn is not None else None
             F.add("bn_apply", lambda: ops.bn_train_apply(z, bn.tr, y, relu, residual, rtr, BN_MOMENTUM, BN_EPS,
-                                                         self.bn_scale, bn.sync_fwd, rsync), 0, _nb(z, y, residual))
+                                                         self.bn_scale), 0, _nb(z, y, residual))
         elif res_bn is not None:
             F.add("bn_apply", lambda: ops.bn_apply(z, bn.scale, bn.shift, y, relu, residual, res_bn.scale,
                                                    res_bn.shift), 0, _nb(z, y, residual))
@@ -238,8 +218,6 @@ class Plan:
 
     def sync_stats(self, F, bn):
         """SyncBN forward: sum the per-rank [sum, sum^2] before the BN apply pass reads them"""
-        if self.sync_nvlink and self.sync_fused:
-            return      # the exchange runs in the prologue of the apply pass
         if self.sync_nvlink:
             F.add("bn_exchange", lambda: L.fcall(
                 "mcb_sync_exchange", self._stats_arena.data_ptr(), self._peer_recv_stats.data_ptr(), self.rank, self.world,
@@ -252,8 +230,6 @@ class Plan:
         """SyncBN backward: dz needs the GLOBAL dbeta / dgamma.  They are the parameter-gradient slots themselves, so
         after this they hold the global sums on every rank (FusedTrainStep divides them by the world size before the
         arena-wide gradient all-reduce adds the ranks up again)."""
-        if self.sync_nvlink and self.sync_fused:
-            return      # the exchange runs in the prologue of the dz pass
         if self.sync_nvlink:
             B.add("bn_exchange", lambda: L.fcall(
                 "mcb_sync_exchange", self._dstats_loc.data_ptr(), self._peer_recv_dstats.data_ptr(), self.rank, self.world,
@@ -286,7 +262,7 @@ class Plan:
                   0, _nb(dy, ymask, z))
         self.sync_bn_grads(B, bn)
         B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(dy, ymask, z, bn.mean, bn.invstd, bn.gamma, bn.app_dbeta,
-                                                      bn.app_dgamma, dz, g_out, g_out_acc, self.bn_scale, bn.sync_bwd), 0,
+                                                      bn.app_dgamma, dz, g_out, g_out_acc, self.bn_scale), 0,
               _nb(dy, ymask, z, dz, g_out))
         desc = "%d->%d k%d s%d @%dx%dx%d" % (x.shape[3], dz.shape[3], k, s, x.shape[0], x.shape[1], x.shape[2])
         B.add("conv_wgrad", lambda: ops.conv_wgrad(dz, x, gw, k, s), 2.0 * dz.numel() * x.shape[3] * k * k,
@@ -362,7 +338,7 @@ class Plan:
                 self.sync_bn_grads(B, bn0)
                 B.add("bn_bwd_apply", lambda: ops.bn_bwd_apply(d_a0, a0, z0, bn0.mean, bn0.invstd, bn0.gamma,
                                                               bn0.app_dbeta, bn0.app_dgamma, dz0, None, False,
-                                                              self.bn_scale, bn0.sync_bwd),
+                                                              self.bn_scale),
                       0, _nb(d_a0, a0, z0, dz0))
                 B.add("misc", lambda: L.zero(stem_gw))
                 B.add("conv_wgrad", lambda: ops.conv_wgrad(dz0, col, stem_gw, 1, 1), sflops, _nb(dz0, col))
@@ -675,7 +651,11 @@ BN_EPS = 1e-5
 
 
 class UNetFunction(torch.autograd.Function):
-    """autograd bridge: logits = UNet(x); backward fills the gradient arena and hands its views to the parameters"""
+    """autograd bridge: logits = UNet(x); backward fills the gradient arena and hands its views to the parameters.
+    Limitation (differs from torch): the arena is zeroed by every backward pass, so a SECOND backward() before
+    optimizer.step() / zero_grad() replaces the gradients instead of accumulating into them -- the reference's
+    _fit_loop (one backward per step, src/steps/pytorch/models.py:105-111) never does that; gradient accumulation
+    over micro-batches needs the fused train step to grow an accumulate flag."""
 
     @staticmethod
     def forward(ctx, x, net, plan, *params):

@@ -221,17 +221,14 @@ def make_bn_train(stats, gamma, beta, rm, rv, mean, invstd):
     return b
 
 
-def bn_train_apply(z, bn, out, relu=True, residual=None, res_bn=None, momentum=0.1, eps=1e-5, count_scale=1,
-                   sync=None, res_sync=None):
+def bn_train_apply(z, bn, out, relu=True, residual=None, res_bn=None, momentum=0.1, eps=1e-5, count_scale=1):
     """bn / res_bn: L.BNTrain structs (make_bn_train); statistics finalisation folded into the apply pass.
-    count_scale = world size when the statistics have been all-reduced (synchronised BatchNorm); sync / res_sync:
-    L.SyncDesc of the one-shot NVLink exchange to run in the kernel's own prologue (bn.stats must point at its `out`)"""
+    count_scale = world size when the statistics have been all-reduced (synchronised BatchNorm)"""
     c = z.shape[-1]
     pixels = z.numel() // c
-    L.fcall("mcb_bn_train_apply_sync", _chk(z).data_ptr(), C.byref(bn), L.dp(residual),
+    L.fcall("mcb_bn_train_apply_global", _chk(z).data_ptr(), C.byref(bn), L.dp(residual),
             C.byref(res_bn) if res_bn is not None else None, int(relu), _chk(out).data_ptr(), pixels,
-            pixels * int(count_scale), c, momentum, eps, C.byref(sync) if sync is not None else None,
-            C.byref(res_sync) if res_sync is not None else None)
+            pixels * int(count_scale), c, momentum, eps)
     return out
 
 
@@ -241,13 +238,12 @@ def bn_bwd_reduce(dy, y_mask, z, mean, invstd, dbeta, dgamma):
             invstd.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), z.numel() // c, c)
 
 
-def bn_bwd_apply(dy, y_mask, z, mean, invstd, gamma, dbeta, dgamma, dz, g_out=None, g_accumulate=False, count_scale=1,
-                 sync=None):
+def bn_bwd_apply(dy, y_mask, z, mean, invstd, gamma, dbeta, dgamma, dz, g_out=None, g_accumulate=False, count_scale=1):
     c = z.shape[-1]
     pixels = z.numel() // c
-    L.fcall("mcb_bn_bwd_apply_sync", _chk(dy).data_ptr(), L.dp(y_mask), _chk(z).data_ptr(), mean.data_ptr(),
+    L.fcall("mcb_bn_bwd_apply_global", _chk(dy).data_ptr(), L.dp(y_mask), _chk(z).data_ptr(), mean.data_ptr(),
             invstd.data_ptr(), gamma.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), _chk(dz).data_ptr(), L.dp(g_out),
-            int(g_accumulate), pixels, pixels * int(count_scale), c, C.byref(sync) if sync is not None else None)
+            int(g_accumulate), pixels, pixels * int(count_scale), c)
 
 
 def channel_sum(x, out):

@@ -3,9 +3,10 @@
 /root/reference/src/augmentation.py:40-86 (PadFixed) and /root/reference/src/preparation.py:151-195 (two-nearest
 building distances, component-size map).
 
-Out of scope: JPEG / PNG decoding, COCO polygon rasterisation (pycocotools), the random imgaug augmenters, and the
-PIL-resampled `resize` loader mode (the bench's crop_and_pad mode pads instead).  Everything here is batched device
-work in libmcb200.so (csrc/input.cu); no CPU fallback."""
+Both loader modes are covered: `crop_and_pad` (PadFixed) and `resize` (transforms.Resize on the PIL image = Pillow's
+8-bit bilinear resampler, restated bit-exactly).  Out of scope: JPEG / PNG decoding, COCO polygon rasterisation
+(pycocotools), the random imgaug augmenters.  Everything here is batched device work in libmcb200.so (csrc/input.cu); no
+CPU fallback."""
 import numpy as np
 import torch
 
@@ -28,6 +29,63 @@ def image_transform_batch(images, pad=(0, 0), pad_method="replicate", mean=MEAN,
     s = (L.C.c_float * 3)(*[float(np.float32(v)) for v in std])
     L.fcall("mcb_image_pad_normalize", x.data_ptr(), out.data_ptr(), n, h, w, ph, pw, PAD_MODES[pad_method], m, s)
     return out
+
+
+_PIL_PRECISION = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR filter (support 1, widened by the scale
+    factor when shrinking): -> (coef int32 (out, ksize), bounds int32 (out, 2) = (first source index, taps))"""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    coef = np.zeros((out_size, ksize), np.int32)
+    bounds = np.zeros((out_size, 2), np.int32)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = np.zeros(ksize)
+        for x in range(xmax):
+            a = abs((x + xmin - center + 0.5) * ss)
+            w[x] = 1.0 - a if a < 1.0 else 0.0
+        ww = w[:xmax].sum()
+        if ww != 0.0:
+            w[:xmax] /= ww
+        k = w * (1 << _PIL_PRECISION)
+        coef[xx] = np.where(w < 0, k - 0.5, k + 0.5).astype(np.int64).astype(np.int32)   # C double -> int: truncation
+        bounds[xx] = (xmin, xmax)
+    return coef, bounds
+
+
+_PIL_TABLES = {}
+
+
+def pil_resize_batch(images, size):
+    """transforms.Resize(size) on PIL images (src/loaders.py:287-305): images (N, H, W, C) uint8 -> (N, h, w, C) uint8 cuda,
+    bit-identical to Image.resize((w, h), BILINEAR)"""
+    x = _to_dev(images, torch.uint8)
+    n, h, w, c = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    key = (x.device, h, w, oh, ow)
+    if key not in _PIL_TABLES:
+        ch, bh = pil_bilinear_coeffs(w, ow)
+        cv, bv = pil_bilinear_coeffs(h, oh)
+        _PIL_TABLES[key] = tuple(torch.from_numpy(a).to(x.device) for a in (ch, bh, cv, bv)) + (ch.shape[1], cv.shape[1])
+    ch, bh, cv, bv, kh, kv = _PIL_TABLES[key]
+    tmp = torch.empty((n, h, ow, c), dtype=torch.uint8, device=x.device)
+    out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+    L.fcall("mcb_pil_resize_bilinear_u8", x.data_ptr(), tmp.data_ptr(), out.data_ptr(), ch.data_ptr(), bh.data_ptr(), kh,
+            cv.data_ptr(), bv.data_ptr(), kv, n, h, w, c, oh, ow)
+    return out
+
+
+def image_transform_resize_batch(images, size, mean=MEAN, std=STD):
+    """the `resize` loader mode's image_transform (src/loaders.py:291-295): Resize -> ToTensor -> Normalize"""
+    return image_transform_batch(pil_resize_batch(images, size), (0, 0), "replicate", mean, std)
 
 
 def two_nearest_distances(instance_masks):

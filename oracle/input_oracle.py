@@ -65,3 +65,13 @@ def target(mask, distances, sizes, pad=(0, 0), pad_method="replicate"):
     s = np.sqrt(sizes.astype(np.uint16)).astype(np.uint16)
     chans = [pad_image(c.astype(np.uint8), pad, pad_method).astype(np.float32) for c in (mask, d, s)]
     return np.stack(chans)
+
+
+def pil_resize(img, size):
+    """transforms.Resize(size) on a PIL image: the REAL Pillow resampler (Pillow is installed wherever the tests run)"""
+    from PIL import Image
+    return np.array(Image.fromarray(img).resize((int(size[1]), int(size[0])), Image.BILINEAR))
+
+
+def image_transform_resize(img, size):
+    return image_transform(pil_resize(img, size))

@@ -57,3 +57,20 @@ def test_size_matrix_and_target_tensor_bit_exact(mcb, cuda):
     for pad, method in (((10, 10), "replicate"), ((0, 0), "replicate")):
         got = prep.target_batch(mask[None], dsum[None], big[None], pad, method).cpu().numpy()[0]
         assert np.array_equal(got, IO.target(mask, dsum, big, pad, method)), pad
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(300, 300, 256, 256), (37, 53, 20, 31), (64, 64, 64, 64), (50, 40, 80, 90)])
+def test_pil_bilinear_resize_bit_exact(mcb, cuda, h, w, oh, ow):
+    """the `resize` loader mode (neptune.yaml default): transforms.Resize on a PIL image, against Pillow itself"""
+    from mcb200 import preparation as prep
+    rs = np.random.RandomState(h + ow)
+    imgs = rs.randint(0, 256, (2, h, w, 3)).astype(np.uint8)
+    got = prep.pil_resize_batch(imgs, (oh, ow)).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(got[i], IO.pil_resize(imgs[i], (oh, ow)))
+    full = prep.image_transform_resize_batch(imgs, (oh, ow)).cpu().numpy()
+    assert np.array_equal(full[0], IO.image_transform_resize(imgs[0], (oh, ow)))
+    mask = (rs.rand(1, h, w, 1) > 0.6).astype(np.uint8)                       # single-band targets resize the same way
+    got1 = prep.pil_resize_batch(mask, (oh, ow)).cpu().numpy()[0, :, :, 0]
+    from PIL import Image
+    assert np.array_equal(got1, np.array(Image.fromarray(mask[0, :, :, 0]).resize((ow, oh), Image.BILINEAR)))

@@ -68,9 +68,6 @@ def test_replicas_stay_identical_with_per_replica_batchnorm(mcb, two_gpus):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.skipif(os.environ.get("MCB_TEST_SYNC_BN") != "1",
-                    reason="synchronised BatchNorm is an opt-in that has not run on hardware yet (DESIGN.md section 5): "
-                           "set MCB_TEST_SYNC_BN=1 on a >= 2-GPU box")
 @pytest.mark.parametrize("mode", [2, 1])
 def test_sync_bn_reproduces_the_single_process_global_batch(mcb, two_gpus, mode):
     """mode 1: one NCCL all-reduce per BatchNorm; mode 2: the one-shot exchange over NVLink peer memory (csrc/sync.cu)"""
