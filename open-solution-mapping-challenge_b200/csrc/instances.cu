@@ -361,6 +361,7 @@ extern "C" int mcb_instance_geometry(const int* labels, const void* prob, int pr
 extern "C" int mcb_rle_walk(const int* labels, const int* offsets, const int* geo, const int* inst_plane,
                             const int* task_slot, const int* task_x, const int* task_start, int* task_n, int* changes,
                             int* spans, int ntasks, int h, int w, int write, void* stream) {
+  if (ntasks <= 0) return MCB_OK;   // every instance empty: nothing to walk
   MCB_REQUIRE(labels && offsets && geo && inst_plane && task_slot && task_x && task_n, "rle_walk: null pointer");
   MCB_REQUIRE(!write || (task_start && changes && spans), "rle_walk: write pass needs task_start, changes, spans");
   MCB_REQUIRE((long)h * w < (1L << 31), "rle_walk: plane too large");
