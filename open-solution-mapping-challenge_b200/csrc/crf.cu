@@ -34,7 +34,9 @@ constexpr int CRF_T = 32;                 // outputs per CTA edge
 constexpr int CRF_S = CRF_T + 2 * CRF_R;  // staged tile edge (44)
 constexpr int CRF_ROWS = 4;               // outputs per thread (vertical)
 constexpr int CRF_THREADS = CRF_T * (CRF_T / CRF_ROWS);   // 256
-constexpr size_t CRF_SMEM = (size_t)CRF_S * CRF_S * (sizeof(float4) + sizeof(float4) + sizeof(float2)) +
+// 73 KB per CTA -> three CTAs per SM (the first version kept Q*n_b duplicated as float4: 104 KB, two CTAs, 24 % warp
+// occupancy in the ncu capture profiles/r02_ncu_full_summary.md)
+constexpr size_t CRF_SMEM = (size_t)CRF_S * CRF_S * (sizeof(float4) + sizeof(float2) + sizeof(float2)) +
                             (size_t)CRF_S * CRF_T * sizeof(float2);
 
 __constant__ float c_g1g[CRF_D];    // 1-D spatial weights exp(-d^2 / (2 sxy^2)), Gaussian kernel
@@ -69,9 +71,9 @@ __global__ void __launch_bounds__(CRF_THREADS) crf_kernel(const float* __restric
                                                           float compat_g, float compat_b, int first_iter) {
   extern __shared__ __align__(16) uint8_t crf_smem[];
   float4(*s_rgb)[CRF_S] = reinterpret_cast<float4(*)[CRF_S]>(crf_smem);                      // scaled r, g, b, -
-  float4(*s_qb)[CRF_S] = reinterpret_cast<float4(*)[CRF_S]>(crf_smem + sizeof(float4) * CRF_S * CRF_S);  // q0 q0 q1 q1 (x n_b)
-  float2(*s_qg)[CRF_S] = reinterpret_cast<float2(*)[CRF_S]>(crf_smem + 2 * sizeof(float4) * CRF_S * CRF_S);  // q0 q1 (x n_g)
-  float2(*s_hg)[CRF_T] = reinterpret_cast<float2(*)[CRF_T]>(crf_smem + (2 * sizeof(float4) + sizeof(float2)) * CRF_S * CRF_S);
+  float2(*s_qb)[CRF_S] = reinterpret_cast<float2(*)[CRF_S]>(crf_smem + sizeof(float4) * CRF_S * CRF_S);  // q0 q1 (x n_b)
+  float2(*s_qg)[CRF_S] = reinterpret_cast<float2(*)[CRF_S]>(crf_smem + (sizeof(float4) + sizeof(float2)) * CRF_S * CRF_S);  // q0 q1 (x n_g)
+  float2(*s_hg)[CRF_T] = reinterpret_cast<float2(*)[CRF_T]>(crf_smem + (sizeof(float4) + 2 * sizeof(float2)) * CRF_S * CRF_S);
   const int img = blockIdx.z;
   const long hw = (long)H * W;
   const int x0 = blockIdx.x * CRF_T, y0 = blockIdx.y * CRF_T;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(CRF_THREADS) crf_kernel(const float* __restric
     const int sy = i / CRF_S, sx = i % CRF_S;
     const int y = y0 + sy - CRF_R, x = x0 + sx - CRF_R;
     float4 c = make_float4(1e9f, 1e9f, 1e9f, 0.f);   // outside the image: the colour weight underflows to exactly 0
-    float4 qb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 qb = make_float2(0.f, 0.f);
     float2 qg = make_float2(0.f, 0.f);
     if (y >= 0 && y < H && x >= 0 && x < W) {
       const long p = (long)y * W + x;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(CRF_THREADS) crf_kernel(const float* __restric
         }
         const float a = ng[p], b = nb[p];
         qg = make_float2(q0 * a, q1 * a);
-        qb = make_float4(q0 * b, q0 * b, q1 * b, q1 * b);
+        qb = make_float2(q0 * b, q1 * b);
       } else {
         qg = make_float2(1.f, 1.f);   // MODE 0: the separable pass then sums the in-image Gaussian weights
       }
@@ -150,8 +152,12 @@ __global__ void __launch_bounds__(CRF_THREADS) crf_kernel(const float* __restric
     for (int d = 0; d < CRF_D; ++d) {
       const float4 o = s_rgb[ry + s][lane + d];
       const f2 orr = pk(o.x, o.x), og = pk(o.y, o.y), ob = pk(o.z, o.z);
-      float4 q;
-      if (MODE == 1) q = s_qb[ry + s][lane + d];
+      f2 q0p = 0ull, q1p = 0ull;   // (q0, q0), (q1, q1): the register moves ride on the otherwise idle ALU pipe
+      if (MODE == 1) {
+        const float2 q = s_qb[ry + s][lane + d];
+        q0p = pk(q.x, q.x);
+        q1p = pk(q.y, q.y);
+      }
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr) {
         const f2 dr = sub2(mr[pr], orr), dg = sub2(mg[pr], og), db = sub2(mb[pr], ob);
@@ -162,8 +168,8 @@ __global__ void __launch_bounds__(CRF_THREADS) crf_kernel(const float* __restric
         upk(t, t0, t1);
         const f2 k = pk(ex2_approx(-t0), ex2_approx(-t1));
         if (MODE == 1) {
-          r0[pr] = fma2(k, pk(q.x, q.y), r0[pr]);
-          r1[pr] = fma2(k, pk(q.z, q.w), r1[pr]);
+          r0[pr] = fma2(k, q0p, r0[pr]);
+          r1[pr] = fma2(k, q1p, r1[pr]);
         } else {
           r0[pr] = add2(r0[pr], k);
         }

@@ -126,3 +126,51 @@ def test_nms_and_features(mcb, cuda):
                     assert a[k] == b[k], (k, a[k], b[k])
                 for k in ("mean_prob", "max_prob", "bbox_ar", "bbox_fill"):
                     assert abs(a[k] - b[k]) <= 1e-9 * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+def test_tta_inference_pipeline_end_to_end(mcb, cuda):
+    """unet_tta (src/pipelines.py:94-155) on the device: generator -> 16 index-map variants of the batch -> network ->
+    ONE aggregation kernel on the raw logits (softmax + inverse maps + gmean) -> centre crop -> MaskPostprocessor ->
+    create_annotations.  The fused aggregation must equal the reference's chain (numpy softmax per variant, per-channel
+    inverse transforms, scipy gmean) applied to the SAME network outputs, and the emitted RLEs must decode back to the
+    label maps."""
+    import bench
+    from mcb200 import loaders as lo, ops, postprocessing as pp, utils as U
+    from mcb200.models import PyTorchUNet
+    from oracle import unet_oracle as O
+    sd = O.make_reference_like_state_dict(34, seed=11)
+    model = PyTorchUNet(**bench.unet_config("ResNet34"))
+    model.model.load_state_dict(sd)
+    model._to_device()
+    net = model.model
+    net.eval()
+    x, _ = synthetic.train_batch(2, 64, seed=4, n_rect=5)
+    gen = lo.TestTimeAugmentationGenerator(flip_ud=True, flip_lr=True, rotation=True, color_shift_runs=False)
+    meta = gen.transform([["a"], ["b"]])
+    params, ids = meta["tta_params"], meta["img_ids"]
+    assert len(params) == 32
+    X = torch.from_numpy(x).to(cuda)
+    Xv = lo.test_time_augmentation_transform_batch(X, params, ids)
+    with torch.no_grad():
+        logits = net(Xv)
+    fused = lo.aggregate_batch(logits.contiguous(), params, ids, "gmean", from_logits=True).cpu().numpy()
+    probs = ops.softmax2(logits.contiguous()).cpu().numpy()
+    want = np.stack(I.tta_aggregate(list(probs), params, ids, "gmean"))
+    assert fused.shape == (2, 2, 64, 64) and np.abs(fused - want).max() < 2e-6
+    # a flip-equivariance sanity check of the index maps: the variant-0 prediction is the plain prediction
+    with torch.no_grad():
+        plain = ops.softmax2(net(X).contiguous()).cpu().numpy()
+    assert np.abs(probs[0] - plain[0]).max() < 1e-6 and np.abs(probs[16] - plain[1]).max() < 1e-6
+    # downstream: crop -> chain -> annotations; RLEs decode to the label maps
+    out = pp.MaskPostprocessor((56, 56), "crop", 0, 0).transform(torch.from_numpy(fused))["y_pred"]
+    ann = U.create_annotations([7, 8], out, None, [None, 100], [1, 1])
+    k = 0
+    for image_id, (labels, scores) in zip([7, 8], out):
+        for l in range(1, int(labels[1].max()) + 1):
+            a = ann[k]
+            k += 1
+            assert a["image_id"] == image_id and a["category_id"] == 100
+            cnts = U.rle_string_to_counts(a["segmentation"]["counts"])
+            flat = np.concatenate([np.full(c, i % 2, np.uint8) for i, c in enumerate(cnts)])
+            assert np.array_equal(flat.reshape(56, 56).T.astype(bool), labels[1] == l)
+    assert k == len(ann)
