@@ -216,8 +216,11 @@ def create_annotations(meta, predictions, logger, category_ids, category_layers,
     if logger is not None:
         logger.info('Creating annotations')
     category_layers_inds = np.cumsum(category_layers)
-    image_ids = list(meta["ImageId"].values) if hasattr(meta, "__getitem__") and not isinstance(meta, (list, tuple)) \
-        else list(meta)
+    if isinstance(meta, (list, tuple, np.ndarray)):
+        image_ids = list(meta)                       # plain ids (tests / callers without a metadata frame)
+    else:
+        ids = meta["ImageId"]                        # the reference's pd.DataFrame (src/utils.py:97)
+        image_ids = list(getattr(ids, "values", ids))
     planes, owners = [], []
     for image_id, (prediction, image_scores) in zip(image_ids, predictions):
         for category_ind, (category_instances, category_scores) in enumerate(zip(prediction, image_scores)):
