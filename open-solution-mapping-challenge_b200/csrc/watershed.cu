@@ -15,11 +15,12 @@ namespace mcb {
 
 constexpr int WS_T = 32;
 constexpr int WS_INF = 0x3fffffff;
+constexpr int WS_MAX_TILES = 1024;   // tile-activity table in shared memory (larger planes sweep every tile)
 
 template <int STAGE>
 __device__ void ws_stage(const int* __restrict__ lev, int* __restrict__ cost, int* __restrict__ dist,
                          int* __restrict__ lab, const int* __restrict__ markers, const uint8_t* __restrict__ mask, int H,
-                         int W) {
+                         int W, const unsigned char* __restrict__ tile_on) {
   __shared__ int s_var[WS_T + 2][WS_T + 2];   // the variable being relaxed in this stage
   __shared__ int s_cost[WS_T + 2][WS_T + 2];  // stage >= 2
   __shared__ int s_dist[WS_T + 2][WS_T + 2];  // stage 3
@@ -32,6 +33,7 @@ __device__ void ws_stage(const int* __restrict__ lev, int* __restrict__ cost, in
     int sweep_changed = 0;
     for (int ti = 0; ti < ntiles; ++ti) {
       const int t = (sweep & 1) ? (ntiles - 1 - ti) : ti;
+      if (tile_on != nullptr && !tile_on[t]) continue;   // no mask / marker pixel in this tile: nothing can change
       const int x0 = (t % tiles_x) * WS_T, y0 = (t / tiles_x) * WS_T;
       // stage the tile + halo
       for (int i = threadIdx.x; i < (WS_T + 2) * (WS_T + 2); i += blockDim.x) {
@@ -120,11 +122,27 @@ __global__ void __launch_bounds__(WS_T* WS_T) watershed_kernel(const T* __restri
     lab[i] = m > 0 ? m : WS_INF;
   }
   __syncthreads();
-  ws_stage<1>(lev, cost, dist, lab, mk, ms, H, W);
+  // tiles without a single mask / marker pixel never hold an active pixel in any stage: mark them once, skip them in
+  // every sweep (building maps cover ~20 % of a tile map)
+  __shared__ unsigned char s_tile_on[WS_MAX_TILES];
+  const int tiles_x = (W + WS_T - 1) / WS_T, tiles_y = (H + WS_T - 1) / WS_T;
+  const unsigned char* tile_on = nullptr;
+  if (tiles_x * tiles_y <= WS_MAX_TILES) {
+    const int tx = threadIdx.x % WS_T, ty = threadIdx.x / WS_T;
+    for (int t = 0; t < tiles_x * tiles_y; ++t) {
+      const int x = (t % tiles_x) * WS_T + tx, y = (t / tiles_x) * WS_T + ty;
+      const bool on = (x < W && y < H) && (ms[(long)y * W + x] != 0 || mk[(long)y * W + x] > 0);
+      const int any = __syncthreads_or(on ? 1 : 0);
+      if (threadIdx.x == 0) s_tile_on[t] = (unsigned char)(any != 0);
+    }
+    __syncthreads();
+    tile_on = s_tile_on;
+  }
+  ws_stage<1>(lev, cost, dist, lab, mk, ms, H, W, tile_on);
   __syncthreads();
-  ws_stage<2>(lev, cost, dist, lab, mk, ms, H, W);
+  ws_stage<2>(lev, cost, dist, lab, mk, ms, H, W, tile_on);
   __syncthreads();
-  ws_stage<3>(lev, cost, dist, lab, mk, ms, H, W);
+  ws_stage<3>(lev, cost, dist, lab, mk, ms, H, W, tile_on);
   __syncthreads();
   for (long i = threadIdx.x; i < hw; i += blockDim.x)
     if (lab[i] >= WS_INF) lab[i] = 0;
