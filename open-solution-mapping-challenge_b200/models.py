@@ -516,9 +516,10 @@ class FusedTrainStep:
         else:
             segs += [(lambda sg=sg: self._seg_backward(sg)) for sg in self.segments]
         gs = []
+        from .engine import graph_capture
         for seg in segs:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with graph_capture(g, self.dev):      # main chain on a high-priority stream (engine.stream_priority_enabled)
                 seg()
             gs.append(g)
         self.graphs = gs
