@@ -242,7 +242,7 @@ class Model:
             batch_loss = loss_function(out, target) * weight
             batch_loss.backward()
             self.optimizer.step()
-            return {'sum': batch_loss.detach()}
+            return {'sum': batch_loss.detach().reshape(1)}   # shape (1,), like the fused path (callbacks index [0])
         self._fused = self._fused_step(net, X.shape, target.shape, spec)
         group = self.optimizer.param_groups[0]
         loss = self._fused.step(X, target, lr=group['lr'], betas=group.get('betas', (0.9, 0.999)),
